@@ -1,0 +1,140 @@
+/*
+ * windgym_b200.h -- C-ABI of the B200-native batched wind-farm environment hot path.
+ *
+ * Drop-in boundary for the per-step hot path of DTUWindEnergy/WindGym.  The reference is pure Python and has
+ * no FFI of its own; every entry point below cites the reference interface it replaces.
+ * All pointers named "device" are CUDA device pointers owned by the caller (torch tensors in the Python host
+ * layer); the library allocates nothing per step, never synchronises the host, and is not re-entrant per
+ * handle (one handle per GPU / stream).  Every function returns 0 on success or a negative wg_status; the
+ * message of the last failure on the calling thread is available from wg_last_error().
+ */
+#ifndef WINDGYM_B200_H
+#define WINDGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WG_VERSION 100
+
+typedef enum {
+  WG_OK = 0,
+  WG_ERR_INVALID = -1,   /* bad argument / configuration (reference raises ValueError) */
+  WG_ERR_UNSUPPORTED = -2, /* reference raises NotImplementedError (e.g. ActionMethod "absolute") */
+  WG_ERR_CUDA = -3,      /* CUDA runtime failure, message has the cudaError string */
+  WG_ERR_NO_DEVICE = -4  /* no sm_100 device: the product path never falls back to the CPU */
+} wg_status;
+
+/* One scalar history of MesClass.Mes (WindGym/MesClass.py:34-52). */
+typedef struct {
+  int32_t current;        /* return the latest sample                      */
+  int32_t rolling_mean;   /* return history_N window means                 */
+  int32_t history_N;
+  int32_t history_length; /* deque maxlen                                  */
+  int32_t window_length;
+} wg_mes_channel;
+
+/* farm_mes constructor arguments (WindGym/MesClass.py:360-401, built at Wind_Farm_Env.py:409-451). */
+typedef struct {
+  wg_mes_channel ws, wd, yaw, power;
+  int32_t turb_ws, turb_wd, turb_TI, turb_power, farm_ws, farm_wd, farm_TI, farm_power;
+  /* scaling ranges of _scale_val (MesClass.py:324-326); double so that float32(hi - lo) rounds like numpy */
+  double ws_min, ws_max, wd_min, wd_max, yaw_min, yaw_max, ti_min, ti_max, power_max;
+  int32_t noise;          /* 0 "None", 1 "Normal" (MesClass.py:441-444)     */
+  float noise_std[4];     /* ws, wd, yaw, power (MesClass.py:436-439)       */
+  uint64_t noise_seed;    /* the reference's noise RNG is unseeded; ours is counter based */
+  int32_t multi_agent;    /* 0: WindFarmEnv obs vector (MesClass.py:679-703);
+                             1: WindFarmEnvMulti per-agent rows (WindEnvMulti.py:79-103) */
+} wg_mes_config;
+
+/* Everything WindFarmEnv.__init__ / load_config fixes for the lifetime of an env (Wind_Farm_Env.py:50-261,:349-399). */
+typedef struct {
+  int32_t n_envs;         /* B: independent farm instances in the batch      */
+  int32_t n_turb;         /* T = nx*ny                                       */
+  int32_t n_farms;        /* 1, or 2 when Baseline_comp (Wind_Farm_Env.py:217-220) */
+  int32_t p_cap;          /* wake-particle slots per turbine chain (multiple of 8) */
+  int32_t substeps;       /* sim_steps_per_env_step = dt_env/dt_sim (:105)   */
+  float dt;               /* dt_sim [s]                                      */
+  float diameter;         /* turbine.diameter()  (:244)                      */
+  float hub_height;       /* turbine.hub_height() (:475)                     */
+  float d_particle;       /* 0.2 (:116)                                      */
+  int32_t n_tab;          /* power/CT table knots (py_wake PowerCtTabular)   */
+  const float* tab_ws;    /* host pointers, copied by wg_create              */
+  const float* tab_power; /* [W]                                             */
+  const float* tab_ct;
+  const double* x_pos;    /* host, layout frame, [T] (:246-252)              */
+  const double* y_pos;
+  int32_t action_method;  /* 0 "yaw", 1 "wind" (:828-858); "absolute" -> WG_ERR_UNSUPPORTED (:861) */
+  float yaw_min, yaw_max, yaw_step;
+  int32_t base_controller; /* 0 "Local", 1 "Global" (BasicControllers.py:10,:49) */
+  int32_t power_reward;   /* 0 "None", 1 "Baseline", 2 "Power_avg", 3 "Power_diff" (:173-194) */
+  int32_t power_avg;      /* deque maxlen (:142-143)                         */
+  float power_scaling;
+  float action_penalty;
+  int32_t action_penalty_type; /* 0 "Change", 1 "Total" (:804-820)           */
+  int32_t steps_on_reset; /* (:229-240)                                      */
+  wg_mes_config mes;
+} wg_config;
+
+/* Per-env inputs of WindFarmEnv.reset (Wind_Farm_Env.py:680-802).  All device pointers.  The integer fields are
+ * computed by the host in fp64 exactly as the reference does (:727-732), so that no discrete decision depends
+ * on device rounding. */
+typedef struct {
+  const uint8_t* mask;       /* [B] 1 = reset this env; NULL = all                      */
+  const float* ws;           /* [B] _set_windconditions (:557-585)                      */
+  const float* ti_flow;      /* [B] TI seen by the flow solver (0 for turbtype "None")  */
+  const float* wd;           /* [B]                                                     */
+  const float* yaw0;         /* [B,T] initial yaw offsets (:715-720)                    */
+  const float* rated_power;  /* [B] turbine.power(ws) (:700)                            */
+  const int32_t* k_emit;     /* [B] particle release cadence in flow steps              */
+  const int32_t* t_developed;/* [B] int(2*dist/ws)/dt spin-up flow steps (:729,:734)    */
+  const int32_t* time_max;   /* [B] int(t_inflow*n_passthrough) (:732); 9999999 for FarmEval */
+} wg_reset_args;
+
+typedef struct wg_handle wg_handle;
+
+/* WindFarmEnv.__init__: copies the immutable tables to the current CUDA device. */
+int wg_create(const wg_config* cfg, wg_handle** out);
+void wg_destroy(wg_handle* h);
+const char* wg_last_error(void);
+int wg_version(void);
+
+/* Size of the caller-owned state buffer (one per handle; zero-initialised by the caller). */
+int wg_state_bytes(const wg_handle* h, size_t* out);
+/* observed_variables() (MesClass.py:610-618); per agent when mes.multi_agent. */
+int wg_obs_dim(const wg_handle* h, int32_t* out);
+/* Introspection of the state layout so the host can expose fs.windTurbines.{yaw,power(),rotor_avg_windspeed},
+ * fs.time ... as tensor views (AgentEval.py:193-209).  dtype: 0 = f32, 1 = i32.  Returns WG_ERR_INVALID for an
+ * unknown name; names are listed by wg_state_field_name(i). */
+int wg_state_field(const wg_handle* h, const char* name, size_t* offset, int32_t* dtype, int32_t* ndim,
+                   int64_t shape[8]);
+const char* wg_state_field_name(const wg_handle* h, int32_t index);
+
+/* WindFarmEnv.reset for the masked envs: spin-up fs.run(t_developed), measurement fill, first observation.
+ * obs: device [B, obs_dim] (single agent) or [B, T, obs_dim] (multi agent); rows of unmasked envs untouched. */
+int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, void* cuda_stream);
+
+/* WindFarmEnv.step (Wind_Farm_Env.py:920-1034) for all envs.  actions: device [B,T] in [-1,1].
+ * reward: device [B]; truncated: device [B] (terminated is always False in the reference, :1029). */
+int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
+            void* cuda_stream);
+
+/* DWMFlowSimulation.step()/run() alone (dynamiks seam, call sites Wind_Farm_Env.py:734,:745,:945): advance the
+ * flow of every env by n_steps with the current yaws; no measurement bookkeeping. */
+int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream);
+
+/* farm_mes.add_measurements + get_measurements(scaled=True) + clip (MesClass.py:568-591,:679-703;
+ * Wind_Farm_Env.py:513-520) on the state's ring buffers.  ws/wd/yaw/power: device [B,T]. */
+int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float* wd, const float* yaw,
+                        const float* power, float* obs, void* cuda_stream);
+
+/* Number of kernel launches issued through this handle so far (bench.py "gpu_launches"). */
+int wg_launch_count(const wg_handle* h, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WINDGYM_B200_H */

@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): per-step power within 1e-4 relative of the fp64 oracle; observations are
+float32 in the reference, compared at 2e-5 absolute on the [-1, 1] scale; integer bookkeeping bit-exact.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_rollout, rich_config, small_config
+
+pytestmark = pytest.mark.gpu
+
+POWER_RTOL = 1e-4
+OBS_ATOL = 2e-5
+
+
+def _conditions(B, T, seed, wd_lo=258.0, wd_hi=282.0):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(7, 14, B), rng.uniform(0.02, 0.15, B), rng.uniform(wd_lo, wd_hi, B),
+            rng.uniform(-15, 15, (B, T)))
+
+
+def _run_gpu(cfg, ws, ti, wd, yaw0, acts, **kw):
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    B, T = yaw0.shape
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", **kw)
+    obs0, _ = env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    out = dict(obs0=obs0.cpu().numpy().copy(), obs=[], reward=[], power=[], yaw=[], trunc=[], power_base=[], yaw_base=[])
+    for a in acts:
+        o, r, _, tr, info = env.step(torch.as_tensor(a))
+        out["obs"].append(o.cpu().numpy().copy()); out["reward"].append(r.cpu().numpy().copy())
+        out["trunc"].append(tr.cpu().numpy().copy())
+        out["power"].append(info["Power pr turbine agent"].cpu().numpy().copy())
+        out["yaw"].append(info["yaw angles agent"].cpu().numpy().copy())
+        if env.Baseline_comp:
+            out["power_base"].append(info["Power pr turbine baseline"].cpu().numpy().copy())
+            out["yaw_base"].append(info["yaw angles base"].cpu().numpy().copy())
+    env.check_flags()
+    out = {k: np.array(v) for k, v in out.items()}
+    return env, out
+
+
+def _compare(gpu, ref, B, baseline=False):
+    # gpu arrays are [steps, B, ...]; oracle arrays are [B, steps, ...]
+    for b in range(B):
+        p_g, p_r = gpu["power"][:, b], ref["power"][b]
+        rel = np.abs(p_g - p_r) / np.maximum(np.abs(p_r), 1.0)
+        assert rel.max() < POWER_RTOL, f"env {b}: power rel err {rel.max():.3e}"
+        assert np.allclose(gpu["yaw"][:, b], ref["yaw"][b], atol=1e-4), f"env {b}: yaw"
+        assert np.allclose(gpu["obs0"][b], ref["obs0"][b], atol=OBS_ATOL), f"env {b}: reset obs"
+        assert np.allclose(gpu["obs"][:, b], ref["obs"][b], atol=OBS_ATOL), \
+            f"env {b}: obs max err {np.abs(gpu['obs'][:, b] - ref['obs'][b]).max():.3e}"
+        assert np.allclose(gpu["reward"][:, b], ref["reward"][b], rtol=2e-4, atol=2e-5), f"env {b}: reward"
+        assert np.array_equal(gpu["trunc"][:, b].astype(bool), ref["trunc"][b].astype(bool)), f"env {b}: truncated"
+        if baseline:
+            relb = np.abs(gpu["power_base"][:, b] - ref["power_base"][b]) / np.maximum(ref["power_base"][b], 1.0)
+            assert relb.max() < POWER_RTOL, f"env {b}: baseline power rel err {relb.max():.3e}"
+            assert np.allclose(gpu["yaw_base"][:, b], ref["yaw_base"][b], atol=1e-3), f"env {b}: baseline yaw"
+
+
+@pytest.mark.parametrize("nx,ny,action", [(2, 1, "yaw"), (2, 2, "wind"), (3, 2, "wind")])
+def test_step_parity_power_avg(built_lib, nx, ny, action):
+    T, B, steps = nx * ny, 3, 8
+    cfg = small_config(nx, ny, reward="Power_avg", action=action)
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=10 + T)
+    acts = np.random.default_rng(1).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    _, gpu = _run_gpu(cfg, ws, ti, wd, yaw0, acts)
+    ref = oracle_rollout(cfg, ws, ti, wd, yaw0, acts)
+    _compare(gpu, ref, B)
+
+
+def test_step_parity_baseline_farm(built_lib):
+    """Power_reward 'Baseline': second farm with the greedy local controller (Wind_Farm_Env.py:948-954)."""
+    nx, ny, B, steps = 2, 2, 3, 8
+    cfg = small_config(nx, ny, reward="Baseline", action="wind")
+    ws, ti, wd, yaw0 = _conditions(B, nx * ny, seed=3)
+    acts = np.random.default_rng(2).uniform(-1, 1, (steps, B, nx * ny)).astype(np.float32)
+    env, gpu = _run_gpu(cfg, ws, ti, wd, yaw0, acts)
+    assert env.n_farms == 2
+    ref = oracle_rollout(cfg, ws, ti, wd, yaw0, acts)
+    _compare(gpu, ref, B, baseline=True)
+
+
+def test_step_parity_substeps_and_penalty(built_lib):
+    """dt_env = 3*dt_sim (substep means, Wind_Farm_Env.py:943-969) + 'Change' action penalty (:804-820)."""
+    cfg = small_config(2, 2, reward="Power_avg", action="yaw", **{"act_pen.action_penalty": 0.05})
+    B, T, steps = 2, 4, 5
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=5)
+    acts = np.random.default_rng(3).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    _, gpu = _run_gpu(cfg, ws, ti, wd, yaw0, acts, dt_env=3, dt_sim=1)
+    ref = oracle_rollout(cfg, ws, ti, wd, yaw0, acts, dt_env=3, dt_sim=1)
+    _compare(gpu, ref, B)
+
+
+def test_rich_observation_parity(built_lib):
+    """All measurement channels, current + several windows, TI, farm level (MesClass.py:328-351, :679-703)."""
+    cfg = rich_config(2, 2, reward="Power_avg")
+    B, T, steps = 2, 4, 6
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=8)
+    acts = np.random.default_rng(4).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    env, gpu = _run_gpu(cfg, ws, ti, wd, yaw0, acts)
+    ref = oracle_rollout(cfg, ws, ti, wd, yaw0, acts)
+    assert env.obs_var == ref["obs"].shape[-1]
+    _compare(gpu, ref, B)
+
+
+def test_flow_state_matches_oracle_particles(built_lib):
+    """Raw wake state after fs.run(n): particle positions and Ainslie profiles, chain by chain, age by age."""
+    from oracle import dwm_numpy as dwm
+    from oracle.v80 import V80 as OV80
+    from windgym_b200 import V80, VecWindFarmEnv
+    from windgym_b200.config import grid_layout
+    cfg = small_config(2, 2)
+    B, T = 2, 4
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=21)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", fill_window=False)
+    env.reset(wind=(ws, ti, wd), yaw0=yaw0)  # spin-up + 1 fill step
+    n_spin, _, _ = env.ec.reset_integers(ws, wd)
+    x, y = grid_layout(80.0, 4, 4, 2, 2)
+    for b in range(B):
+        wt = dwm.PyWakeWindTurbines(x, y, OV80())
+        fs = dwm.DWMFlowSimulation(dwm.TurbulenceFieldSite(ws[b], dwm.RandomTurbulence(0, ws[b])), wt,
+                                   wind_direction=wd[b], dt=1, d_particle=0.2)
+        wt.yaw = yaw0[b]
+        for _ in range(int(n_spin[b]) + 1):
+            fs.step()
+        assert int(env.state["n_step"][b, 0]) == fs.n_step
+        for t in range(T):
+            prof, pmut, pcon = env.profiles_by_age(b, 0, t)
+            sl = fs.slots_by_age(t)
+            assert prof.shape[0] == len(sl), (b, t, prof.shape[0], len(sl))
+            assert np.allclose(pmut[:, :2], fs.pmut[t, sl, :2], atol=2e-2), "particle positions"
+            assert np.abs(prof - fs.prof[t, sl]).max() < 2e-5, f"profiles max err {np.abs(prof - fs.prof[t, sl]).max():.2e}"
+            assert np.allclose(pcon, fs.pcon[t, sl], atol=1e-4), "emission scalars"
+        assert np.allclose(env.state["u"][b, 0].cpu().numpy(), fs.rotor_avg_windspeed[:, 0], rtol=2e-5)

@@ -1,0 +1,421 @@
+// C-ABI of libwindgym_b200 (declared in include/windgym_b200.h): handle, state layout, launch orchestration.
+// Host-side only; the kernels live in flow.cu and env.cu.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "wg_internal.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(WG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct Field {
+  std::string name;
+  size_t offset;
+  int32_t dtype;  // 0 f32, 1 i32
+  std::vector<int64_t> shape;
+};
+
+}  // namespace
+
+struct wg_handle {
+  wg_config cfg;
+  wg::Dev dev;  // template: table pointers + dims set, state pointers filled per call from the state base
+  std::vector<Field> fields;
+  size_t state_bytes = 0;
+  int hist_max = 0;
+  uint64_t launches = 0;
+  // device-resident immutable tables
+  float *d_tab_ws = nullptr, *d_tab_p = nullptr, *d_tab_ct = nullptr;
+  double *d_x = nullptr, *d_y = nullptr;
+  int *d_ring_off = nullptr, *d_ring_chan = nullptr;
+  wg::ObsDesc* d_desc = nullptr;
+};
+
+namespace {
+
+size_t add_field(wg_handle* h, const char* name, int32_t dtype, std::vector<int64_t> shape) {
+  size_t n = 4;
+  for (auto s : shape) n *= (size_t)s;
+  size_t off = (h->state_bytes + 255) / 256 * 256;
+  h->fields.push_back({name, off, dtype, shape});
+  h->state_bytes = off + n;
+  return off;
+}
+
+const Field* find_field(const wg_handle* h, const char* name) {
+  for (auto& f : h->fields)
+    if (f.name == name) return &f;
+  return nullptr;
+}
+
+template <class Tp>
+Tp* at(void* base, const wg_handle* h, const char* name) {
+  return reinterpret_cast<Tp*>(reinterpret_cast<unsigned char*>(base) + find_field(h, name)->offset);
+}
+
+wg::Dev bind(const wg_handle* h, void* state) {
+  wg::Dev d = h->dev;
+  d.prof = at<float>(state, h, "prof");
+  d.pmut = at<float>(state, h, "pmut");
+  d.pcon = at<float>(state, h, "pcon");
+  d.head = at<int>(state, h, "head");
+  d.count = at<int>(state, h, "count");
+  d.n_step = at<int>(state, h, "n_step");
+  d.yaw = at<float>(state, h, "yaw");
+  d.u = at<float>(state, h, "u");
+  d.v = at<float>(state, h, "v");
+  d.w = at<float>(state, h, "w");
+  d.power = at<float>(state, h, "power");
+  d.ct = at<float>(state, h, "ct");
+  d.ws = at<float>(state, h, "ws");
+  d.ti = at<float>(state, h, "ti");
+  d.wd = at<float>(state, h, "wd");
+  d.rated = at<float>(state, h, "rated_power");
+  d.xmax = at<float>(state, h, "xmax");
+  d.k_emit = at<int>(state, h, "k_emit");
+  d.time_max = at<int>(state, h, "time_max");
+  d.timestep = at<int>(state, h, "timestep");
+  d.flags = at<int>(state, h, "flags");
+  d.n_push = at<int>(state, h, "n_push");
+  d.n_fp = at<int>(state, h, "n_fp");
+  d.n_bp = at<int>(state, h, "n_bp");
+  d.spin = at<int>(state, h, "spin");
+  d.xr = at<float>(state, h, "xr");
+  d.yr = at<float>(state, h, "yr");
+  d.meas = at<float>(state, h, "meas");
+  d.base_pow_mean = at<float>(state, h, "base_pow_mean");
+  d.old_yaw = at<float>(state, h, "old_yaw");
+  d.rings = at<float>(state, h, "rings");
+  d.fp_ring = at<float>(state, h, "farm_pow_ring");
+  d.bp_ring = at<float>(state, h, "base_pow_ring");
+  return d;
+}
+
+template <class Tp>
+cudaError_t upload(Tp** dst, const Tp* src, size_t n) {
+  cudaError_t e = cudaMalloc(dst, sizeof(Tp) * (n ? n : 1));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*dst, src, sizeof(Tp) * n, cudaMemcpyHostToDevice);
+}
+
+int chan_outputs(const wg_mes_channel& c, int gate) { return gate ? (c.current ? 1 : 0) + (c.rolling_mean ? c.history_N : 0) : 0; }
+
+// Observation descriptor list: order of farm_mes.get_measurements (MesClass.py:679-703) or, for the multi-agent
+// layout, of WindFarmEnvMulti._get_obs_multi (WindEnvMulti.py:79-103).
+void build_desc(const wg_config& cfg, std::vector<wg::ObsDesc>& out, int& obs_dim, int& obs_rows) {
+  const wg_mes_config& m = cfg.mes;
+  const int T = cfg.n_turb;
+  const wg_mes_channel* ch[4] = {&m.ws, &m.wd, &m.yaw, &m.power};
+  const double lo[4] = {m.ws_min, m.wd_min, m.yaw_min, 0.0};
+  const double hi[4] = {m.ws_max, m.wd_max, m.yaw_max, m.power_max};
+  auto emit_chan = [&](std::vector<wg::ObsDesc>& v, int c, int ring, int gate, double l, double h) {
+    if (!gate) return;
+    wg::ObsDesc d{};
+    d.ring = ring; d.chan = c; d.lo = (float)l; d.span = (float)(h - l);
+    if (ch[c]->current) { d.kind = 0; d.win = 0; v.push_back(d); }
+    if (ch[c]->rolling_mean)
+      for (int i = 0; i < ch[c]->history_N; ++i) { d.kind = 1; d.win = i; v.push_back(d); }
+  };
+  auto turb_block = [&](std::vector<wg::ObsDesc>& v, int t) {  // turb_mes.get_measurements order: ws|wd|yaw|TI|power
+    emit_chan(v, 0, 0 * T + t, m.turb_ws, lo[0], hi[0]);
+    emit_chan(v, 1, 1 * T + t, m.turb_wd, lo[1], hi[1]);
+    emit_chan(v, 2, 2 * T + t, 1, lo[2], hi[2]);
+    if (m.turb_TI) {
+      wg::ObsDesc d{};
+      d.kind = 2; d.ring = t; d.chan = 0; d.lo = (float)m.ti_min; d.span = (float)(m.ti_max - m.ti_min);
+      v.push_back(d);
+    }
+    emit_chan(v, 3, 3 * T + t, m.turb_power, lo[3], hi[3]);
+  };
+  const int fr = 4 * T;  // farm rings: ws, wd, power
+  if (!m.multi_agent) {
+    for (int t = 0; t < T; ++t) turb_block(out, t);
+    emit_chan(out, 0, fr + 0, m.farm_ws, lo[0], hi[0]);
+    emit_chan(out, 1, fr + 1, m.farm_wd, lo[1], hi[1]);
+    if (m.farm_TI) {
+      wg::ObsDesc d{};
+      d.kind = 3; d.chan = 0; d.lo = (float)m.ti_min; d.span = (float)(m.ti_max - m.ti_min);
+      out.push_back(d);
+    }
+    emit_chan(out, 3, fr + 2, m.farm_power, lo[3], hi[3] * T);
+    obs_rows = 1;
+    obs_dim = (int)out.size();
+  } else {
+    // farm block = farm-level turb_mes.get_measurements(scaled=True); its yaw history never receives data
+    // (MesClass.py:588-591) so it contributes nothing; its TI is calc_TI of the farm ws ring.
+    std::vector<wg::ObsDesc> farm;
+    emit_chan(farm, 0, fr + 0, m.farm_ws, lo[0], hi[0]);
+    emit_chan(farm, 1, fr + 1, m.farm_wd, lo[1], hi[1]);
+    if (m.farm_TI) {
+      wg::ObsDesc d{};
+      d.kind = 2; d.ring = fr + 0; d.chan = 0; d.lo = (float)m.ti_min; d.span = (float)(m.ti_max - m.ti_min);
+      farm.push_back(d);
+    }
+    emit_chan(farm, 3, fr + 2, m.farm_power, lo[3], hi[3] * T);
+    for (int t = 0; t < T; ++t) {
+      turb_block(out, t);
+      out.insert(out.end(), farm.begin(), farm.end());
+    }
+    obs_rows = T;
+    obs_dim = (int)out.size() / T;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wg_last_error(void) { return g_last_error.c_str(); }
+int wg_version(void) { return WG_VERSION; }
+
+int wg_create(const wg_config* cfg, wg_handle** out) {
+  if (!cfg || !out) return fail(WG_ERR_INVALID, "wg_create: null argument");
+  *out = nullptr;
+  if (cfg->n_envs < 1) return fail(WG_ERR_INVALID, "n_envs must be >= 1");
+  if (cfg->n_turb < 1 || cfg->n_turb > WG_MAX_T) return fail(WG_ERR_INVALID, "n_turb must be in 1..64");
+  if (cfg->n_farms < 1 || cfg->n_farms > 2) return fail(WG_ERR_INVALID, "n_farms must be 1 or 2");
+  if (cfg->p_cap < 8 || cfg->p_cap % 8) return fail(WG_ERR_INVALID, "p_cap must be a positive multiple of 8");
+  if (cfg->substeps < 1) return fail(WG_ERR_INVALID, "dt_env must be a multiple of dt_sim");
+  if (!(cfg->dt > 0.f) || !(cfg->diameter > 0.f)) return fail(WG_ERR_INVALID, "dt and diameter must be positive");
+  if (cfg->n_tab < 2 || !cfg->tab_ws || !cfg->tab_power || !cfg->tab_ct || !cfg->x_pos || !cfg->y_pos)
+    return fail(WG_ERR_INVALID, "turbine tables / layout missing");
+  if (cfg->action_method == 2) return fail(WG_ERR_UNSUPPORTED, "The absolute method is not implemented yet");
+  if (cfg->action_method < 0 || cfg->action_method > 2)
+    return fail(WG_ERR_INVALID, "The ActionMethod must be yaw, wind or absolute");
+  if (cfg->power_reward < 0 || cfg->power_reward > 3)
+    return fail(WG_ERR_INVALID, "The Power_reward must be either Baseline, Power_avg, None or Power_diff");
+  if (cfg->power_reward == 3 && cfg->power_avg < 40)
+    return fail(WG_ERR_INVALID, "The Power_avg must be larger then 40 for the Power_diff reward.");
+  if (cfg->power_reward == 1 && cfg->n_farms != 2) return fail(WG_ERR_INVALID, "Baseline reward needs n_farms == 2");
+  if (cfg->n_farms == 2 && (cfg->base_controller < 0 || cfg->base_controller > 1))
+    return fail(WG_ERR_INVALID, "The BaseController must be either Local or Global... For now");
+  if (cfg->power_avg < 1) return fail(WG_ERR_INVALID, "Power_avg must be >= 1");
+  const wg_mes_channel* ch[4] = {&cfg->mes.ws, &cfg->mes.wd, &cfg->mes.yaw, &cfg->mes.power};
+  for (int c = 0; c < 4; ++c)
+    if (ch[c]->history_length < 1 || ch[c]->window_length < 1 || ch[c]->history_N < 1)
+      return fail(WG_ERR_INVALID, "measurement history_length / window_length / history_N must be >= 1");
+  if (cfg->steps_on_reset < 1) return fail(WG_ERR_INVALID, "fill_window must be True or a non-negative integer");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(WG_ERR_NO_DEVICE, "no CUDA device visible: windgym_b200 has no CPU fallback");
+  int devid = 0;
+  cudaGetDevice(&devid);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, devid);
+  if (prop.major != 10)
+    return fail(WG_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is not sm_100 (Blackwell B200) class");
+
+  wg_handle* h = new wg_handle();
+  h->cfg = *cfg;
+  const int B = cfg->n_envs, T = cfg->n_turb, F = cfg->n_farms, P = cfg->p_cap;
+  cudaError_t e;
+  if ((e = upload(&h->d_tab_ws, cfg->tab_ws, cfg->n_tab)) != cudaSuccess ||
+      (e = upload(&h->d_tab_p, cfg->tab_power, cfg->n_tab)) != cudaSuccess ||
+      (e = upload(&h->d_tab_ct, cfg->tab_ct, cfg->n_tab)) != cudaSuccess ||
+      (e = upload(&h->d_x, cfg->x_pos, T)) != cudaSuccess || (e = upload(&h->d_y, cfg->y_pos, T)) != cudaSuccess) {
+    wg_destroy(h);
+    return cuda_fail(e, "wg_create upload");
+  }
+  h->cfg.tab_ws = h->cfg.tab_power = h->cfg.tab_ct = nullptr;
+  h->cfg.x_pos = h->cfg.y_pos = nullptr;
+
+  // ring table: turbine rings c*T+t (c = ws, wd, yaw, power), then farm ws / wd / power
+  std::vector<int> ring_off, ring_chan;
+  int off = 0;
+  for (int c = 0; c < 4; ++c)
+    for (int t = 0; t < T; ++t) { ring_off.push_back(off); ring_chan.push_back(c); off += ch[c]->history_length; }
+  const int fch[3] = {0, 1, 3};
+  for (int k = 0; k < 3; ++k) { ring_off.push_back(off); ring_chan.push_back(fch[k]); off += ch[fch[k]]->history_length; }
+  std::vector<wg::ObsDesc> desc;
+  int obs_dim = 0, obs_rows = 1;
+  build_desc(*cfg, desc, obs_dim, obs_rows);
+  if ((e = upload(&h->d_ring_off, ring_off.data(), ring_off.size())) != cudaSuccess ||
+      (e = upload(&h->d_ring_chan, ring_chan.data(), ring_chan.size())) != cudaSuccess ||
+      (e = upload(&h->d_desc, desc.data(), desc.size())) != cudaSuccess) {
+    wg_destroy(h);
+    return cuda_fail(e, "wg_create upload");
+  }
+  // rotor quadrature: 4 equal-area rings x 4 azimuths (oracle/dwm_numpy.py:rotor_points)
+  float qy[WG_NQ], qz[WG_NQ];
+  for (int k = 0; k < 4; ++k)
+    for (int m = 0; m < 4; ++m) {
+      const double rho = std::sqrt((k + 0.5) / 4.0);
+      const double phi = 2.0 * M_PI * (m + 0.5 * (k & 1)) / 4.0 + M_PI / 8.0;
+      qy[4 * k + m] = (float)(rho * std::cos(phi));
+      qz[4 * k + m] = (float)(rho * std::sin(phi));
+    }
+  wg::set_rotor_points(qy, qz);
+
+  wg::Dev& d = h->dev;
+  memset(&d, 0, sizeof(d));
+  d.B = B; d.T = T; d.F = F; d.P = P; d.S = cfg->substeps; d.n_tab = cfg->n_tab;
+  d.dt = cfg->dt; d.D = cfg->diameter; d.R = 0.5f * cfg->diameter; d.zh = cfg->hub_height; d.d_particle = cfg->d_particle;
+  d.yaw_min = cfg->yaw_min; d.yaw_max = cfg->yaw_max; d.yaw_step = cfg->yaw_step;
+  d.action_method = cfg->action_method; d.base_controller = cfg->base_controller;
+  d.power_reward = cfg->power_reward; d.power_avg = cfg->power_avg; d.pen_type = cfg->action_penalty_type;
+  d.power_scaling = cfg->power_scaling; d.action_penalty = cfg->action_penalty;
+  d.n_rings = (int)ring_off.size(); d.ring_floats = off; d.obs_dim = obs_dim; d.obs_rows = obs_rows;
+  for (int c = 0; c < 4; ++c) {
+    d.ch_cur[c] = ch[c]->current; d.ch_roll[c] = ch[c]->rolling_mean; d.ch_N[c] = ch[c]->history_N;
+    d.ch_H[c] = ch[c]->history_length; d.ch_W[c] = ch[c]->window_length;
+    d.noise_std[c] = cfg->mes.noise_std[c];
+  }
+  d.noise = cfg->mes.noise; d.noise_seed = cfg->mes.noise_seed;
+  d.ti_lo = (float)cfg->mes.ti_min; d.ti_span = (float)(cfg->mes.ti_max - cfg->mes.ti_min);
+  d.ring_off = h->d_ring_off; d.ring_chan = h->d_ring_chan; d.obs_desc = h->d_desc;
+  d.tab_ws = h->d_tab_ws; d.tab_p = h->d_tab_p; d.tab_ct = h->d_tab_ct; d.x_pos = h->d_x; d.y_pos = h->d_y;
+  h->hist_max = std::max(std::max(cfg->mes.ws.history_length, cfg->mes.wd.history_length), cfg->mes.yaw.history_length);
+
+  add_field(h, "prof", 0, {B, F, T, P, WG_NR});
+  add_field(h, "pmut", 0, {2, B, F, T, P, 4});
+  add_field(h, "pcon", 0, {B, F, T, P, 4});
+  add_field(h, "head", 1, {B, F, T});
+  add_field(h, "count", 1, {B, F, T});
+  add_field(h, "n_step", 1, {B, F});
+  for (const char* n : {"yaw", "u", "v", "w", "power", "ct"}) add_field(h, n, 0, {B, F, T});
+  for (const char* n : {"ws", "ti", "wd", "rated_power", "xmax", "base_pow_mean"}) add_field(h, n, 0, {B});
+  for (const char* n : {"k_emit", "time_max", "timestep", "flags", "n_push", "n_fp", "n_bp", "spin"})
+    add_field(h, n, 1, {B});
+  add_field(h, "xr", 0, {B, T});
+  add_field(h, "yr", 0, {B, T});
+  add_field(h, "meas", 0, {B, 4, T});
+  add_field(h, "old_yaw", 0, {B, T});
+  add_field(h, "rings", 0, {B, off});
+  add_field(h, "farm_pow_ring", 0, {B, cfg->power_avg});
+  add_field(h, "base_pow_ring", 0, {B, cfg->power_avg});
+  h->state_bytes = (h->state_bytes + 255) / 256 * 256;
+  *out = h;
+  return WG_OK;
+}
+
+void wg_destroy(wg_handle* h) {
+  if (!h) return;
+  cudaFree(h->d_tab_ws); cudaFree(h->d_tab_p); cudaFree(h->d_tab_ct); cudaFree(h->d_x); cudaFree(h->d_y);
+  cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc);
+  delete h;
+}
+
+int wg_state_bytes(const wg_handle* h, size_t* out) {
+  if (!h || !out) return fail(WG_ERR_INVALID, "wg_state_bytes: null argument");
+  *out = h->state_bytes;
+  return WG_OK;
+}
+
+int wg_obs_dim(const wg_handle* h, int32_t* out) {
+  if (!h || !out) return fail(WG_ERR_INVALID, "wg_obs_dim: null argument");
+  *out = h->dev.obs_dim;
+  return WG_OK;
+}
+
+int wg_state_field(const wg_handle* h, const char* name, size_t* offset, int32_t* dtype, int32_t* ndim, int64_t shape[8]) {
+  if (!h || !name || !offset || !dtype || !ndim || !shape) return fail(WG_ERR_INVALID, "wg_state_field: null argument");
+  const Field* f = find_field(h, name);
+  if (!f) return fail(WG_ERR_INVALID, std::string("unknown state field '") + name + "'");
+  *offset = f->offset; *dtype = f->dtype; *ndim = (int32_t)f->shape.size();
+  for (size_t i = 0; i < f->shape.size(); ++i) shape[i] = f->shape[i];
+  return WG_OK;
+}
+
+const char* wg_state_field_name(const wg_handle* h, int32_t index) {
+  if (!h || index < 0 || index >= (int32_t)h->fields.size()) return nullptr;
+  return h->fields[index].name.c_str();
+}
+
+int wg_launch_count(const wg_handle* h, uint64_t* out) {
+  if (!h || !out) return fail(WG_ERR_INVALID, "wg_launch_count: null argument");
+  *out = h->launches;
+  return WG_OK;
+}
+
+#define WG_LAUNCH(expr, what)                                   \
+  do {                                                          \
+    cudaError_t e_ = (expr);                                    \
+    ++h->launches;                                              \
+    if (e_ != cudaSuccess) return cuda_fail(e_, what);          \
+  } while (0)
+
+int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream) {
+  if (!h || !state) return fail(WG_ERR_INVALID, "wg_flow_steps: null argument");
+  if (n_steps < 0) return fail(WG_ERR_INVALID, "n_steps must be >= 0");
+  if (n_steps == 0) return WG_OK;
+  wg::Dev d = bind(h, state);
+  wg::FlowArgs fa{};
+  fa.mode = wg::FLOW_FIXED; fa.n_fixed = n_steps; fa.farm_mask = (1 << d.F) - 1;
+  WG_LAUNCH(wg::launch_flow(d, fa, (cudaStream_t)cuda_stream), "wg_flow_kernel");
+  return WG_OK;
+}
+
+int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, void* cuda_stream) {
+  if (!h || !state || !args || !obs) return fail(WG_ERR_INVALID, "wg_reset: null argument");
+  if (!args->ws || !args->ti_flow || !args->wd || !args->yaw0 || !args->rated_power || !args->k_emit ||
+      !args->t_developed || !args->time_max)
+    return fail(WG_ERR_INVALID, "wg_reset: every per-env input array is required");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  wg::Dev d = bind(h, state);
+  wg::ResetDevArgs ra{args->mask, args->ws, args->ti_flow, args->wd, args->yaw0, args->rated_power,
+                      args->k_emit, args->t_developed, args->time_max};
+  WG_LAUNCH(wg::launch_reset_init(d, ra, s), "wg_reset_init_kernel");
+  // fs.run(t_developed) for the agent farm and the baseline farm (Wind_Farm_Env.py:734, :782)
+  wg::FlowArgs spin{};
+  spin.mode = wg::FLOW_SPIN; spin.mask = args->mask; spin.farm_mask = (1 << d.F) - 1;
+  WG_LAUNCH(wg::launch_flow(d, spin, s), "wg_flow_kernel(spin-up)");
+  // measurement fill: steps_on_reset env steps for the agent farm (:737-766), hist_max for the baseline farm,
+  // whose controller stays off during the fill (:784-796)
+  const int n_agent = h->cfg.steps_on_reset, n_base = d.F > 1 ? h->hist_max : 0;
+  for (int i = 0; i < std::max(n_agent, n_base); ++i) {
+    const int fm = (i < n_agent ? 1 : 0) | (i < n_base ? 2 : 0);
+    wg::FlowArgs fa{};
+    fa.mode = wg::FLOW_STEP; fa.mask = args->mask; fa.farm_mask = fm;
+    WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(fill)");
+    wg::FinishArgs fin{};
+    fin.mask = args->mask;
+    fin.flags = ((fm & 1) ? (wg::FIN_PUSH_MES | wg::FIN_PUSH_FP) : 0) | ((fm & 2) ? wg::FIN_PUSH_BP : 0);
+    WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(fill)");
+  }
+  wg::FinishArgs fin{};
+  fin.mask = args->mask; fin.flags = wg::FIN_OBS; fin.obs = obs;
+  WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(obs)");
+  return WG_OK;
+}
+
+int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
+            void* cuda_stream) {
+  if (!h || !state || !actions || !obs || !reward || !truncated) return fail(WG_ERR_INVALID, "wg_step: null argument");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  wg::Dev d = bind(h, state);
+  wg::FlowArgs fa{};
+  fa.mode = wg::FLOW_STEP; fa.actions = actions; fa.farm_mask = (1 << d.F) - 1; fa.controller_on = 1;
+  WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
+  wg::FinishArgs fin{};
+  fin.flags = wg::FIN_PUSH_MES | wg::FIN_PUSH_FP | (d.F > 1 ? wg::FIN_PUSH_BP : 0) | wg::FIN_OBS | wg::FIN_REWARD;
+  fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
+  WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(step)");
+  return WG_OK;
+}
+
+int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float* wd, const float* yaw,
+                        const float* power, float* obs, void* cuda_stream) {
+  if (!h || !state || !ws || !wd || !yaw || !power || !obs)
+    return fail(WG_ERR_INVALID, "wg_mes_push_extract: null argument");
+  wg::Dev d = bind(h, state);
+  wg::FinishArgs fin{};
+  fin.flags = wg::FIN_PUSH_MES | wg::FIN_OBS | wg::FIN_MEAS_FROM_ARGS;
+  fin.in_ws = ws; fin.in_wd = wd; fin.in_yaw = yaw; fin.in_power = power; fin.obs = obs;
+  WG_LAUNCH(wg::launch_finish(d, fin, (cudaStream_t)cuda_stream), "wg_finish_kernel(mes)");
+  return WG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+// Env-layer kernels: MesClass ring buffers + observation extraction, rewards, truncation, reset bookkeeping.
+// Reference: WindGym/MesClass.py:23-703 (Mes / turb_mes / farm_mes), Wind_Farm_Env.py:513-520 (_get_obs),
+// :804-820 (_action_penalty), :866-918 (rewards), :972-1027 (step tail), :680-732 (reset head).
+// One CTA per env; everything here is a few KB per env, i.e. ~1 % of the flow kernel's traffic.
+#include "wg_internal.cuh"
+
+namespace wg {
+
+// numpy's pairwise summation (contiguous float64, numpy/core/src/umath/loops_utils.h.src) so that window means
+// round exactly like the reference's np.mean on the same samples.
+template <class Get>
+__device__ double pairwise_sum(Get get, int lo, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res += get(lo + i);
+    return res;
+  }
+  if (n <= 128) {
+    double r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = get(lo + k);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] += get(lo + i + k);
+    }
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += get(lo + i);
+    return res;
+  }
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  return pairwise_sum(get, lo, n2) + pairwise_sum(get, lo + n2, n - n2);
+}
+
+// 2*(val-lo)/(hi-lo)-1 evaluated in float32 exactly like numpy does on a float32 array (MesClass.py:324-326)
+__device__ __forceinline__ float scale_f32(float val, float lo, float span) {
+  return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(val, lo)), span), 1.0f);
+}
+
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ float normal_noise(unsigned long long seed, int b, int push, int chan, int t) {
+  unsigned long long k = splitmix(seed ^ splitmix(((unsigned long long)b << 32) ^ (unsigned)push));
+  k = splitmix(k ^ (((unsigned long long)chan << 32) | (unsigned)t));
+  unsigned long long k2 = splitmix(k);
+  double u1 = ((double)(k >> 11) + 1.0) * (1.0 / 9007199254740993.0);
+  double u2 = (double)(k2 >> 11) * (1.0 / 9007199254740992.0);
+  return (float)(sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2));
+}
+
+// window [lo, hi) of rolling value i over a history of length L (MesClass.py:85-116)
+__device__ __forceinline__ void window_bounds(int L, int N, int W, int i, int& lo, int& hi) {
+  if (i == 0) { lo = max(0, L - W); hi = L; return; }
+  if (i == N - 1 && L >= W) { lo = 0; hi = W; return; }
+  if (L < W) { lo = 0; hi = L; return; }
+  int spacing = max(1, (L - W) / (N - 1));
+  int pos = min(i * spacing, L - W);
+  lo = pos; hi = pos + W;
+}
+
+// np.std(u - U) / U over a whole ring (turb_mes.calc_TI, MesClass.py:220-237), float64 like the reference
+template <class Get>
+__device__ float calc_ti(Get get, int L) {
+  double U = pairwise_sum(get, 0, L) / L;
+  auto dev = [&](int k) { return get(k) - U; };
+  double m2 = pairwise_sum(dev, 0, L) / L;
+  auto sq = [&](int k) { double e = (get(k) - U) - m2; return e * e; };
+  double var = pairwise_sum(sq, 0, L) / L;
+  return (float)(sqrt(var) / U);
+}
+
+__global__ void __launch_bounds__(128) wg_finish_kernel(const Dev d, const FinishArgs a) {
+  const int b = blockIdx.x, tid = threadIdx.x, T = d.T;
+  if (a.mask && !a.mask[b]) return;
+  __shared__ float s_val[4][WG_MAX_T];
+  float* rings = d.rings + (size_t)b * d.ring_floats;
+  int np = d.n_push[b];
+
+  if (a.flags & FIN_PUSH_MES) {
+    if (tid < T) {
+      const float* src[4] = {a.in_ws, a.in_wd, a.in_yaw, a.in_power};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v = (a.flags & FIN_MEAS_FROM_ARGS) ? src[c][b * T + tid] : d.meas[(b * 4 + c) * T + tid];
+        if (d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, tid);
+        s_val[c][tid] = v;
+        const int r = c * T + tid;
+        rings[d.ring_off[r] + np % d.ch_H[c]] = v;  // deque.append (MesClass.py:66-68, :580-586)
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {  // farm-level rings: mean ws, mean wd, sum power (MesClass.py:589-591)
+      auto gw = [&](int k) { return (double)s_val[0][k]; };
+      auto gd = [&](int k) { return (double)s_val[1][k]; };
+      auto gp = [&](int k) { return (double)s_val[3][k]; };
+      rings[d.ring_off[4 * T + 0] + np % d.ch_H[0]] = (float)(pairwise_sum(gw, 0, T) / T);
+      rings[d.ring_off[4 * T + 1] + np % d.ch_H[1]] = (float)(pairwise_sum(gd, 0, T) / T);
+      rings[d.ring_off[4 * T + 2] + np % d.ch_H[3]] = (float)pairwise_sum(gp, 0, T);
+      d.n_push[b] = np + 1;
+    }
+    np += 1;
+  }
+  if (tid == 0) {
+    if (a.flags & FIN_PUSH_FP) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977)
+      auto gp = [&](int k) { return (double)d.meas[(b * 4 + 3) * T + k]; };
+      const int n = d.n_fp[b];
+      d.fp_ring[(size_t)b * d.power_avg + n % d.power_avg] = (float)pairwise_sum(gp, 0, T);
+      d.n_fp[b] = n + 1;
+    }
+    if (a.flags & FIN_PUSH_BP) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
+      const int n = d.n_bp[b];
+      d.bp_ring[(size_t)b * d.power_avg + n % d.power_avg] = d.base_pow_mean[b];
+      d.n_bp[b] = n + 1;
+    }
+  }
+  __syncthreads();
+
+  if (a.flags & FIN_OBS) {  // farm_mes.get_measurements(scaled=True) + clip (MesClass.py:679-703, Wind_Farm_Env.py:513-520)
+    const int n_out = d.obs_rows * d.obs_dim;
+    for (int o = tid; o < n_out; o += blockDim.x) {
+      const ObsDesc ds = d.obs_desc[o];
+      float val = 0.f;
+      if (np > 0) {
+        if (ds.kind == 3) {  // farm TI = mean of the (individually scaled) turbine TIs (MesClass.py:670-673)
+          const int H = d.ch_H[0], L = min(np, H);
+          double acc = 0.0;
+          for (int t = 0; t < T; ++t) {
+            const float* rg = rings + d.ring_off[t];
+            auto get = [&](int k) { return (double)rg[(np - L + k) % H]; };
+            acc += (double)scale_f32(calc_ti(get, L), d.ti_lo, d.ti_span);
+          }
+          val = (float)(acc / T);
+        } else {
+          const int c = ds.chan, H = d.ch_H[c], L = min(np, H);
+          const float* rg = rings + d.ring_off[ds.ring];
+          auto get = [&](int k) { return (double)rg[(np - L + k) % H]; };
+          float raw;
+          if (ds.kind == 0) {
+            raw = rg[(np - 1) % H];
+          } else if (ds.kind == 1) {
+            int lo, hi;
+            window_bounds(L, d.ch_N[c], d.ch_W[c], ds.win, lo, hi);
+            raw = (float)(pairwise_sum(get, lo, hi - lo) / (hi - lo));
+          } else {
+            raw = calc_ti(get, L);
+          }
+          val = scale_f32(raw, ds.lo, ds.span);
+        }
+        val = fminf(fmaxf(val, -1.0f), 1.0f);
+      }
+      a.obs[(size_t)b * n_out + o] = val;
+    }
+  }
+
+  if ((a.flags & FIN_REWARD) && tid == 0) {
+    const int PA = d.power_avg;
+    const int nfp = min(d.n_fp[b], PA), nbp = min(d.n_bp[b], PA);
+    const float* fp = d.fp_ring + (size_t)b * PA;
+    const float* bp = d.bp_ring + (size_t)b * PA;
+    bool nan_seen = false;
+    double sfp = 0.0, sbp = 0.0;
+    for (int k = 0; k < nfp; ++k) { sfp += fp[k]; nan_seen |= isnan(fp[k]); }
+    for (int k = 0; k < nbp; ++k) sbp += bp[k];
+    if (nan_seen) atomicOr(&d.flags[b], 1);  // raise Exception("NaN Power") (Wind_Farm_Env.py:980-981)
+    double rew = 0.0;
+    if (d.power_reward == 1) {
+      rew = (sfp / nfp) / (sbp / nbp) - 1.0;
+    } else if (d.power_reward == 2) {
+      rew = (sfp / nfp) / T / (double)d.rated[b];
+    } else if (d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
+      const int ws_ = PA / 10, ntot = d.n_fp[b];
+      auto lg = [&](int k) { return (double)fp[(ntot - nfp + k) % PA]; };
+      double latest = 0.0, oldest = 0.0;
+      int nl = 0, no = 0;
+      for (int k = PA - ws_; k < PA && k < nfp; ++k) { latest += lg(k); ++nl; }
+      for (int k = 0; k < ws_ && k < nfp; ++k) { oldest += lg(k); ++no; }
+      rew = (latest / nl - oldest / no) / T;
+    }
+    rew *= (double)d.power_scaling;
+    if (d.action_penalty >= 0.001f) {
+      double pen = 0.0;
+      const float* yaw = d.yaw + (size_t)b * d.F * T;  // farm 0
+      for (int t = 0; t < T; ++t)
+        pen += (d.pen_type == 0) ? fabs((double)d.old_yaw[b * T + t] - (double)yaw[t]) : fabs((double)yaw[t]);
+      pen /= T;
+      if (d.pen_type == 1) pen /= (double)d.yaw_max;
+      rew -= (double)d.action_penalty * pen;
+    }
+    a.reward[b] = (float)rew;
+    const int ts = d.timestep[b];
+    a.truncated[b] = ts >= d.time_max[b] ? 1 : 0;  // Wind_Farm_Env.py:1003, :1027
+    d.timestep[b] = ts + 1;
+  }
+}
+
+// WindFarmEnv.reset head (Wind_Farm_Env.py:689-732): wind conditions, rotated layout, clean flow + measurement state
+__global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
+  const int b = blockIdx.x, tid = threadIdx.x, T = d.T;
+  if (a.mask && !a.mask[b]) return;
+  const double wdv = (double)a.wd[b];
+  const double th = (270.0 - wdv) * 0.017453292519943295;
+  double mx = 0.0, my = 0.0;
+  for (int t = 0; t < T; ++t) { mx += d.x_pos[t]; my += d.y_pos[t]; }
+  mx /= T; my /= T;
+  const double c = cos(th), s = sin(th);
+  if (tid < T) {
+    const double dx = d.x_pos[tid] - mx, dy = d.y_pos[tid] - my;
+    d.xr[b * T + tid] = (float)(dx * c + dy * s);
+    d.yr[b * T + tid] = (float)(-dx * s + dy * c);
+    const float ws = a.ws[b];
+    const float yaw0 = a.yaw0[b * T + tid];
+    for (int f = 0; f < d.F; ++f) {
+      const int i = (b * d.F + f) * T + tid;
+      d.head[i] = 0; d.count[i] = 0;
+      d.yaw[i] = yaw0; d.u[i] = ws; d.v[i] = 0.f; d.w[i] = 0.f; d.power[i] = 0.f; d.ct[i] = 0.f;
+    }
+    d.old_yaw[b * T + tid] = yaw0;
+    for (int cc = 0; cc < 4; ++cc) d.meas[(b * 4 + cc) * T + tid] = 0.f;
+  }
+  if (tid == 0) {
+    double xm = -1e300;
+    for (int t = 0; t < T; ++t) xm = fmax(xm, (d.x_pos[t] - mx) * c + (d.y_pos[t] - my) * s);
+    d.xmax[b] = (float)xm;
+    d.ws[b] = a.ws[b]; d.ti[b] = a.ti[b]; d.wd[b] = a.wd[b]; d.rated[b] = a.rated[b];
+    d.k_emit[b] = a.k_emit[b]; d.time_max[b] = a.time_max[b]; d.spin[b] = a.t_dev[b];
+    d.timestep[b] = 0; d.n_push[b] = 0; d.flags[b] = 0; d.base_pow_mean[b] = 0.f;
+    for (int f = 0; f < d.F; ++f) d.n_step[b * d.F + f] = 0;
+  }
+}
+
+cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
+  wg_finish_kernel<<<d.B, 128, 0, s>>>(d, a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s) {
+  wg_reset_init_kernel<<<d.B, 64, 0, s>>>(d, a);
+  return cudaGetLastError();
+}
+
+}  // namespace wg

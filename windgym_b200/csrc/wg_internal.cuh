@@ -1,0 +1,108 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI host code of libwindgym_b200.
+// Model constants mirror oracle/dwm_numpy.py (the frozen specification); see DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/windgym_b200.h"
+
+#define WG_NR 64          // radial nodes per wake profile
+#define WG_NQ 16          // rotor quadrature points
+#define WG_MAX_T 64       // turbines per farm supported by the fixed-size shared tables
+#define WG_TILE 32        // stations per warp tile
+#define WG_ROW_BYTES (WG_NR * 4)
+
+namespace wg {
+
+constexpr float DR = 1.0f / 16.0f;
+constexpr float K_HILL = 0.4f;
+constexpr float K1 = 0.023f;
+constexpr float K2 = 0.016f;
+constexpr float CT_MAX = 0.96f;
+constexpr float MARGIN_D = 2.0f;
+constexpr float DXT_MIN = 1e-6f;
+
+enum FlowMode { FLOW_FIXED = 0, FLOW_SPIN = 1, FLOW_STEP = 2 };
+
+// finish-kernel work flags
+enum FinishFlags {
+  FIN_PUSH_MES = 1, FIN_PUSH_FP = 2, FIN_PUSH_BP = 4, FIN_OBS = 8, FIN_REWARD = 16, FIN_MEAS_FROM_ARGS = 32
+};
+
+// One output element of the observation vector (built on the host from wg_mes_config).
+struct ObsDesc {
+  int32_t kind;   // 0 current, 1 window mean, 2 TI of one ring, 3 mean of turbine TIs (scaled individually)
+  int32_t ring;   // ring id (kind 0,1,2)
+  int32_t chan;   // 0 ws, 1 wd, 2 yaw, 3 power
+  int32_t win;    // window index i (kind 1)
+  float lo, span; // scaling: 2*(v-lo)/span-1, span = float32(double(hi)-double(lo))
+};
+
+struct Dev {
+  // dims
+  int B, T, F, P, S, n_tab;
+  float dt, D, R, zh, d_particle;
+  float yaw_min, yaw_max, yaw_step;
+  int action_method, base_controller;
+  int power_reward, power_avg, pen_type;
+  float power_scaling, action_penalty;
+  // mes
+  int n_rings, ring_floats, obs_dim, obs_rows;  // obs_rows = 1 (single agent) or T (multi agent)
+  int ch_cur[4], ch_roll[4], ch_N[4], ch_H[4], ch_W[4];
+  int noise;
+  float noise_std[4];
+  unsigned long long noise_seed;
+  float ti_lo, ti_span;
+  const int* ring_off;    // [n_rings]
+  const int* ring_chan;   // [n_rings]
+  const ObsDesc* obs_desc;  // [obs_rows * obs_dim]
+  // tables
+  const float* tab_ws; const float* tab_p; const float* tab_ct;
+  const double* x_pos; const double* y_pos;
+  // particle state
+  float* prof;   // [B,F,T,P,64]   16-byte chunks XOR-swizzled with (slot & 7)
+  float* pmut;   // [2,B,F,T,P,4]  x, y, z, uc ; ping-pong on the farm's step parity
+  float* pcon;   // [B,F,T,P,4]    U0e, knu1, cos g0, sin g0
+  int* head; int* count;  // [B,F,T]
+  int* n_step;            // [B,F]
+  float *yaw, *u, *v, *w, *power, *ct;  // [B,F,T]
+  // env state
+  float *ws, *ti, *wd, *rated, *xmax;   // [B]
+  int *k_emit, *time_max, *timestep, *flags, *n_push, *n_fp, *n_bp, *spin;  // [B]
+  float *xr, *yr;         // [B,T]
+  float *meas;            // [B,4,T] substep means ws, wd, yaw, power
+  float *base_pow_mean;   // [B]
+  float *old_yaw;         // [B,T]
+  float *rings;           // [B,ring_floats]
+  float *fp_ring, *bp_ring;  // [B,power_avg]
+};
+
+struct FlowArgs {
+  int mode;             // FlowMode
+  int n_fixed;          // FLOW_FIXED: steps for every env
+  const uint8_t* mask;  // optional env mask
+  const float* actions; // FLOW_STEP: [B,T] or null (reset fill)
+  int farm_mask;        // bit f set: farm f advances
+  int controller_on;    // baseline farm applies its greedy controller each substep
+};
+
+struct FinishArgs {
+  int flags;
+  const uint8_t* mask;
+  const float* in_ws; const float* in_wd; const float* in_yaw; const float* in_power;  // FIN_MEAS_FROM_ARGS
+  float* obs; float* reward; uint8_t* truncated;
+};
+
+struct ResetDevArgs {
+  const uint8_t* mask;
+  const float* ws; const float* ti; const float* wd; const float* yaw0; const float* rated;
+  const int* k_emit; const int* t_dev; const int* time_max;
+};
+
+void set_rotor_points(const float* qy, const float* qz);
+size_t flow_smem_bytes(int T, int n_warps);
+cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
+cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
+cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
+
+}  // namespace wg

@@ -1,0 +1,277 @@
+"""VecWindFarmEnv -- thousands of independent WindFarmEnv instances stepped by one CUDA launch.
+
+Batched counterpart of the reference ``WindFarmEnv`` (``WindGym/Wind_Farm_Env.py:47``): same constructor
+arguments, same YAML schema, same ``reset()/step()`` contract, with a leading env axis on every array.
+torch owns all device memory; the compute is ``libwindgym_b200.so`` behind the C-ABI in
+``include/windgym_b200.h`` (no CPU fallback).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import EnvConfig, load_yaml
+
+_TORCH_DT = {0: torch.float32, 1: torch.int32}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class VecWindFarmEnv:
+    def __init__(self, turbine, n_envs, yaml_path=None, config=None, n_passthrough=5, TI_min_mes=0.0,
+                 TI_max_mes=0.50, TurbBox="Default", turbtype="None", Baseline_comp=False, yaw_init=None,
+                 seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True, device="cuda:0",
+                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False):
+        cfg = config if config is not None else load_yaml(yaml_path)
+        self.ec = ec = EnvConfig(cfg, turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes,
+                                 TI_max_mes=TI_max_mes, turbtype=turbtype, Baseline_comp=Baseline_comp,
+                                 yaw_init=yaw_init, dt_sim=dt_sim, dt_env=dt_env, yaw_step=yaw_step,
+                                 fill_window=fill_window, eval_mode=eval_mode, multi_agent=multi_agent,
+                                 noise_seed=noise_seed)
+        self.turbine = turbine
+        self.n_envs, self.n_turb = int(n_envs), ec.n_turb
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.WgError("VecWindFarmEnv runs on a CUDA device only (no CPU fallback)")
+        self.seed = seed
+        self.x_pos, self.y_pos = ec.x_pos, ec.y_pos
+        self.yaw_min, self.yaw_max, self.yaw_step = ec.yaw_min, ec.yaw_max, yaw_step
+        self.Baseline_comp = ec.Baseline_comp
+        self.n_farms = 2 if ec.Baseline_comp else 1
+        self.yaw_initial = [0]
+        self._wind_override = {}
+        self._episode = 0
+        self.lib = _lib.load()
+        torch.cuda.set_device(self.device)
+        self._create()
+        self.obs_shape = (self.n_envs, self.n_turb, self.obs_var) if multi_agent else (self.n_envs, self.obs_var)
+        self.obs = torch.zeros(self.obs_shape, dtype=torch.float32, device=self.device)
+        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
+        self.truncated = torch.zeros(self.n_envs, dtype=torch.uint8, device=self.device)
+        self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=self.device)
+        # host copies of the per-env wind conditions of the current episode
+        self.ws = np.zeros(self.n_envs); self.ti = np.zeros(self.n_envs); self.wd = np.zeros(self.n_envs)
+        if reset_init:
+            self.reset(seed=seed)
+
+    # ------------------------------------------------------------------------------------------ C-ABI plumbing
+    def _create(self):
+        ec, c = self.ec, _lib
+        t = self.turbine
+        self._tabs = [np.ascontiguousarray(a, dtype=np.float32) for a in (t.ws_table, t.power_table_w, t.ct_table)]
+        self._xy = [np.ascontiguousarray(a, dtype=np.float64) for a in (ec.x_pos, ec.y_pos)]
+        codes = ec.codes()
+
+        def chan(m, k):
+            return c.MesChannel(int(m[f"{k}_current"]), int(m[f"{k}_rolling_mean"]), int(m[f"{k}_history_N"]),
+                                int(m[f"{k}_history_length"]), int(m[f"{k}_window_length"]))
+
+        lv = ec.mes_level
+        mes = c.MesConfig(
+            ws=chan(ec.ws_mes, "ws"), wd=chan(ec.wd_mes, "wd"), yaw=chan(ec.yaw_mes, "yaw"),
+            power=chan(ec.power_mes, "power"),
+            turb_ws=int(lv["turb_ws"]), turb_wd=int(lv["turb_wd"]), turb_TI=int(lv["turb_TI"]),
+            turb_power=int(lv["turb_power"]), farm_ws=int(lv["farm_ws"]), farm_wd=int(lv["farm_wd"]),
+            farm_TI=int(lv["farm_TI"]), farm_power=int(lv["farm_power"]),
+            ws_min=2.0, ws_max=25.0, wd_min=ec.wd_min_mes - 5, wd_max=ec.wd_max_mes + 5,  # Wind_Farm_Env.py:440-444
+            yaw_min=ec.yaw_min, yaw_max=ec.yaw_max, ti_min=ec.TI_min_mes, ti_max=ec.TI_max_mes,
+            power_max=ec.maxturbpower, noise=1 if ec.noise == "Normal" else 0,
+            noise_std=(C.c_float * 4)(0.0, 2.0, 0.0, 0.0), noise_seed=int(ec.noise_seed),
+            multi_agent=int(ec.multi_agent))
+        fp = C.POINTER(C.c_float)
+        dp = C.POINTER(C.c_double)
+        cfg = c.Config(
+            n_envs=self.n_envs, n_turb=ec.n_turb, n_farms=self.n_farms, p_cap=ec.p_cap, substeps=ec.S,
+            dt=float(ec.dt_sim), diameter=ec.D, hub_height=ec.hub_height, d_particle=ec.d_particle,
+            n_tab=len(self._tabs[0]), tab_ws=self._tabs[0].ctypes.data_as(fp),
+            tab_power=self._tabs[1].ctypes.data_as(fp), tab_ct=self._tabs[2].ctypes.data_as(fp),
+            x_pos=self._xy[0].ctypes.data_as(dp), y_pos=self._xy[1].ctypes.data_as(dp),
+            action_method=codes["action"], yaw_min=float(ec.yaw_min), yaw_max=float(ec.yaw_max),
+            yaw_step=float(ec.yaw_step), base_controller=codes["controller"], power_reward=codes["reward"],
+            power_avg=int(ec.power_avg), power_scaling=float(ec.Power_scaling),
+            action_penalty=float(ec.action_penalty), action_penalty_type=codes["penalty"],
+            steps_on_reset=int(ec.steps_on_reset), mes=mes)
+        h = C.c_void_p()
+        _lib.check(self.lib.wg_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        nbytes = C.c_size_t()
+        _lib.check(self.lib.wg_state_bytes(h, C.byref(nbytes)))
+        self.state_bytes = nbytes.value
+        self._state = torch.zeros(self.state_bytes, dtype=torch.uint8, device=self.device)
+        od = C.c_int32()
+        _lib.check(self.lib.wg_obs_dim(h, C.byref(od)))
+        self.obs_var = od.value
+        self.state = {}
+        i = 0
+        while True:
+            nm = self.lib.wg_state_field_name(h, i)
+            if nm is None:
+                break
+            off, dt, nd, shp = C.c_size_t(), C.c_int32(), C.c_int32(), (C.c_int64 * 8)()
+            _lib.check(self.lib.wg_state_field(h, nm, C.byref(off), C.byref(dt), C.byref(nd), shp))
+            shape = [shp[k] for k in range(nd.value)]
+            n = int(np.prod(shape)) * 4
+            self.state[nm.decode()] = self._state[off.value:off.value + n].view(_TORCH_DT[dt.value]).view(shape)
+            i += 1
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.wg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self):
+        n = C.c_uint64()
+        _lib.check(self.lib.wg_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ------------------------------------------------------------------------------------------ FarmEval surface
+    def set_wind_vals(self, ws=None, ti=None, wd=None):
+        """FarmEval.set_wind_vals (FarmEval.py:63-78); scalars or per-env arrays."""
+        for k, v in (("ws", ws), ("ti", ti), ("wd", wd)):
+            if v is not None:
+                self._wind_override[k] = np.broadcast_to(np.asarray(v, dtype=np.float64), (self.n_envs,)).copy()
+
+    def set_yaw_vals(self, yaw_vals):
+        self.yaw_initial = yaw_vals
+
+    # ------------------------------------------------------------------------------------------ reset / step
+    def sample_conditions(self, seed=None, envs=None):
+        """Per-env (ws, ti, wd, yaw0) with the reference's draw order ws -> ti -> wd -> yaw (Wind_Farm_Env.py:564-568,
+        :715); env i of episode e uses np.random.default_rng([seed, i, e]) -- and exactly default_rng(seed) for a
+        single env's first episode, which is what gymnasium seeds the reference with."""
+        ec, B, T = self.ec, self.n_envs, self.n_turb
+        envs = range(B) if envs is None else envs
+        ws, ti, wd = self.ws.copy(), self.ti.copy(), self.wd.copy()
+        yaw0 = np.zeros((B, T))
+        for i in envs:
+            if seed is None:
+                rng = np.random.default_rng()
+            elif B == 1 and self._episode == 0:
+                rng = np.random.default_rng(seed)
+            else:
+                rng = np.random.default_rng([seed, i, self._episode])
+            ws[i] = rng.uniform(low=ec.ws_min, high=ec.ws_max)
+            ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
+            wd[i] = rng.uniform(low=ec.wd_min, high=ec.wd_max)
+            if ec.yaw_init_mode == "Random":
+                yaw0[i] = rng.uniform(low=-ec.yaw_start, high=ec.yaw_start, size=T)
+        for k, arr in (("ws", ws), ("ti", ti), ("wd", wd)):
+            if k in self._wind_override:
+                arr[list(envs)] = self._wind_override[k][list(envs)]
+        if ec.yaw_init_mode == "Defined":
+            yv = np.asarray(self.yaw_initial, dtype=np.float64)
+            if yv.size not in (1, T):
+                raise ValueError("So I am pretty sure something has gone wrong here. The specified yaw values "
+                                 "are not the right length.")
+            yaw0[list(envs)] = yv if yv.size == T else np.ones(T) * yv.reshape(-1)[0]
+        return ws, ti, wd, yaw0
+
+    def reset(self, seed=None, mask=None, wind=None, yaw0=None):
+        """WindFarmEnv.reset for the masked envs (all when ``mask`` is None).
+        ``wind=(ws, ti, wd)`` and ``yaw0`` ([B,T]) inject conditions instead of sampling them."""
+        ec, B, T, dev = self.ec, self.n_envs, self.n_turb, self.device
+        sel = np.arange(B) if mask is None else np.flatnonzero(np.asarray(mask))
+        if seed is None:
+            seed = self.seed
+        ws, ti, wd, y0 = self.sample_conditions(seed, sel)
+        if wind is not None:
+            for arr, v in zip((ws, ti, wd), wind):
+                arr[sel] = np.broadcast_to(np.asarray(v, dtype=np.float64), (B,))[sel]
+        if yaw0 is not None:
+            y0[sel] = np.broadcast_to(np.asarray(yaw0, dtype=np.float64), (B, T))[sel]
+        self.ws, self.ti, self.wd = ws, ti, wd
+        n_spin, time_max, k_emit = ec.reset_integers(ws, wd)
+        rated = np.asarray(self.turbine.power(ws), dtype=np.float64)
+        ti_flow = np.zeros(B)  # turbtype "None": RandomTurbulence(ti=0) (Wind_Farm_Env.py:661-665)
+        f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
+        i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev, non_blocking=True)
+        keep = dict(ws=f32(ws), ti=f32(ti_flow), wd=f32(wd), yaw0=f32(y0), rated=f32(rated), k=i32(k_emit),
+                    spin=i32(n_spin), tmax=i32(time_max))
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask), dtype=np.uint8)).to(dev)
+            keep["mask"] = m
+        args = _lib.ResetArgs(mask=_ptr(m), ws=_ptr(keep["ws"]), ti_flow=_ptr(keep["ti"]), wd=_ptr(keep["wd"]),
+                              yaw0=_ptr(keep["yaw0"]), rated_power=_ptr(keep["rated"]), k_emit=_ptr(keep["k"]),
+                              t_developed=_ptr(keep["spin"]), time_max=_ptr(keep["tmax"]))
+        _lib.check(self.lib.wg_reset(self._h, _ptr(self._state), C.byref(args), _ptr(self.obs), self._stream()))
+        self._keep = keep  # inputs stay alive until the stream has consumed them
+        self._episode += 1
+        self.time_max = time_max
+        return self.obs, self._info()
+
+    def step(self, actions):
+        """WindFarmEnv.step for every env: actions float32 [B,T] (device) -> obs, reward, terminated, truncated, info."""
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
+        actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        if actions.numel() != self.n_envs * self.n_turb:
+            raise ValueError(f"actions must have {self.n_envs}x{self.n_turb} elements")
+        _lib.check(self.lib.wg_step(self._h, _ptr(self._state), _ptr(actions), _ptr(self.obs), _ptr(self.reward),
+                                    _ptr(self.truncated), self._stream()))
+        self._last_actions = actions
+        return self.obs, self.reward, self.terminated, self.truncated, self._info()
+
+    def flow_steps(self, n):
+        """DWMFlowSimulation.run(n*dt) for every env and farm, without measurement bookkeeping."""
+        _lib.check(self.lib.wg_flow_steps(self._h, _ptr(self._state), int(n), self._stream()))
+
+    def mes_push_extract(self, ws, wd, yaw, power):
+        """farm_mes.add_measurements + get_measurements(scaled=True) + clip on [B,T] device tensors."""
+        ts = [x.to(self.device, dtype=torch.float32).contiguous() for x in (ws, wd, yaw, power)]
+        _lib.check(self.lib.wg_mes_push_extract(self._h, _ptr(self._state), *[_ptr(x) for x in ts], _ptr(self.obs),
+                                                self._stream()))
+        self._keep_mes = ts
+        return self.obs
+
+    def check_flags(self):
+        """Surface device-side error flags at a sync point (reference: Exception('NaN Power'), Wind_Farm_Env.py:981)."""
+        fl = self.state["flags"]
+        if bool((fl & 1).any()):
+            raise Exception("NaN Power")
+        if bool((fl & 2).any()):
+            raise _lib.WgError("wake particle chain overflow (p_cap too small)")
+
+    def _info(self):
+        """Device views with the reference's info keys (Wind_Farm_Env.py:527-555); zero-copy, no sync."""
+        s = self.state
+        d = {
+            "yaw angles agent": s["yaw"][:, 0], "Wind speed Global": self.ws, "Wind direction Global": self.wd,
+            "Turbulence intensity": self.ti, "Power pr turbine agent": s["power"][:, 0],
+            "Wind speed at turbines": s["meas"][:, 0], "Wind direction at turbines": s["meas"][:, 1],
+            "Turbine x positions": s["xr"], "Turbine y positions": s["yr"],
+        }
+        if self.Baseline_comp:
+            d["yaw angles base"] = s["yaw"][:, 1]
+            d["Power pr turbine baseline"] = s["power"][:, 1]
+            d["Wind speed at turbines baseline"] = s["u"][:, 1]
+        return d
+
+    # helpers for tests / inspection ------------------------------------------------------------------------
+    def profiles_by_age(self, b, f, t):
+        """Un-swizzled wake profiles [count,64] and scalars of one chain, youngest first (host numpy)."""
+        s = self.state
+        P = self.ec.p_cap
+        head, cnt = int(s["head"][b, f, t]), int(s["count"][b, f, t])
+        par = int(s["n_step"][b, f]) & 1
+        slots = (head - 1 - np.arange(cnt)) % P
+        raw = s["prof"][b, f, t].cpu().numpy()[slots].reshape(cnt, 16, 4)
+        key = (slots & 7)[:, None]
+        idx = np.arange(16)[None, :] ^ key
+        prof = np.take_along_axis(raw, idx[:, :, None], axis=1).reshape(cnt, 64)
+        pmut = s["pmut"][par, b, f, t].cpu().numpy()[slots]
+        pcon = s["pcon"][b, f, t].cpu().numpy()[slots]
+        return prof, pmut, pcon
