@@ -134,6 +134,13 @@ int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float*
 /* Number of kernel launches issued through this handle so far (bench.py "gpu_launches"). */
 int wg_launch_count(const wg_handle* h, uint64_t* out);
 
+/* Measurement aid (bench.py "roofline"): when enabled, wg_step records CUDA events on its stream before the flow
+ * kernel, between the two kernels and after the finish kernel.  wg_profile_read waits for the recorded steps,
+ * returns the summed device time of each kernel [ms] and the number of steps, and clears the record.
+ * This is the only entry point that synchronises the host. */
+int wg_profile_enable(wg_handle* h, int32_t on);
+int wg_profile_read(wg_handle* h, double* flow_ms, double* finish_ms, uint64_t* n_steps);
+
 #ifdef __cplusplus
 }
 #endif

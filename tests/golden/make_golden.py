@@ -1,0 +1,191 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference env layer (build container only).
+
+    python tests/golden/make_golden.py
+
+What runs: ``/root/reference/WindGym/{Wind_Farm_Env,MesClass,WindEnv,FarmEval,BasicControllers}.py`` exactly as
+shipped, imported through ``oracle/ref_loader.py`` (import-only shims for gymnasium / matplotlib / ...), over the
+fp64 restatement of the un-vendored ``dynamiks`` seam (``oracle/dwm_numpy.py``, re-exported by
+``oracle/shims/dynamiks``).  So these vectors PIN everything the reference repo itself contains on the hot path
+(MesClass windows/scaling, yaw action semantics, substep means, rewards, truncation, reset bookkeeping, RNG draw
+order, baseline controllers); the flow numbers inside them come from the restated solver (parity unpinned,
+see oracle/dwm_numpy.py).
+
+Files (all small):
+  mes_golden.npz   farm_mes.add_measurements / get_measurements(scaled=True) on seeded random histories
+  env_golden.npz   WindFarmEnv / FarmEval reset + step trajectories on the shipped YAMLs and variants
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_loader import load_reference  # noqa: E402
+from oracle.v80 import V80  # noqa: E402
+from tests.helpers import ENV1, rich_config, small_config  # noqa: E402
+
+
+def mes_cases():
+    """(name, T, farm_mes kwargs, n_push)"""
+    env1 = dict(noise="None", turb_ws=True, turb_wd=False, turb_TI=False, turb_power=False, farm_ws=False,
+                farm_wd=False, farm_TI=False, farm_power=False,
+                ws_current=False, ws_rolling_mean=True, ws_history_N=1, ws_history_length=25, ws_window_length=25,
+                wd_current=False, wd_rolling_mean=False, wd_history_N=1, wd_history_length=20, wd_window_length=20,
+                yaw_current=False, yaw_rolling_mean=True, yaw_history_N=1, yaw_history_length=10, yaw_window_length=10,
+                power_current=False, power_rolling_mean=False, power_history_N=1, power_history_length=10,
+                power_window_length=10,
+                ws_min=2.0, ws_max=25.0, wd_min=250.0, wd_max=290.0, yaw_min=-45, yaw_max=45, TI_min=0.0, TI_max=0.5,
+                power_max=2000000.0)
+    rich = dict(env1, turb_wd=True, turb_TI=True, turb_power=True, farm_ws=True, farm_wd=True, farm_TI=True,
+                farm_power=True, ws_current=True, ws_history_N=3, ws_history_length=12, ws_window_length=4,
+                wd_current=True, wd_rolling_mean=True, wd_history_N=2, wd_history_length=9, wd_window_length=3,
+                yaw_history_N=4, yaw_history_length=10, yaw_window_length=1,
+                power_current=True, power_rolling_mean=True, power_history_N=2, power_history_length=7,
+                power_window_length=7)
+    hist100 = dict(env1, ws_history_N=100, ws_history_length=100, ws_window_length=1,
+                   yaw_rolling_mean=True, yaw_history_N=100, yaw_history_length=100, yaw_window_length=1)
+    spaced = dict(env1, ws_history_N=4, ws_history_length=10, ws_window_length=1, ws_current=True,
+                  yaw_history_N=3, yaw_history_length=25, yaw_window_length=5, farm_ws=True, farm_power=True,
+                  power_rolling_mean=True, power_history_N=5, power_history_length=30, power_window_length=3)
+    return [("env1_T4", 4, env1, 40), ("rich_T3", 3, rich, 30), ("hist100_T2", 2, hist100, 130),
+            ("spaced_T16", 16, spaced, 45)]
+
+
+def make_mes(ns, out):
+    meta = {}
+    for name, T, kw, n_push in mes_cases():
+        fm = ns.MesClass.farm_mes(T, **kw)
+        rng = np.random.default_rng(abs(hash(name)) % 2**31 if False else sum(map(ord, name)))
+        ws = rng.uniform(3.0, 24.0, (n_push, T))
+        wd = rng.uniform(252.0, 288.0, (n_push, T))
+        yaw = rng.uniform(-44.0, 44.0, (n_push, T))
+        pw = rng.uniform(0.0, 2.0e6, (n_push, T))
+        obs = []
+        for k in range(n_push):
+            fm.add_measurements(ws[k].copy(), wd[k].copy(), yaw[k].copy(), pw[k].copy())
+            o = np.clip(fm.get_measurements(scaled=True), -1.0, 1.0).astype(np.float32)  # Wind_Farm_Env.py:513-520
+            obs.append(o)
+        out[f"{name}/ws"], out[f"{name}/wd"], out[f"{name}/yaw"], out[f"{name}/power"] = ws, wd, yaw, pw
+        out[f"{name}/obs"] = np.array(obs)
+        meta[name] = dict(T=T, kwargs=kw, n_push=n_push, observed_variables=int(fm.observed_variables()))
+    out["meta"] = np.array(json.dumps(meta))
+
+
+def write_yaml(cfg):
+    f = tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False)
+    yaml.safe_dump(cfg, f)
+    f.close()
+    return f.name
+
+
+def env_cases(ns):
+    ex = ns.examples
+    with open(os.path.join(ex, "2turb.yaml")) as fh:
+        two = yaml.safe_load(fh)
+    with open(os.path.join(ex, "Env1.yaml")) as fh:
+        env1 = yaml.safe_load(fh)
+    assert env1 == ENV1, "tests/helpers.ENV1 must equal the shipped Env1.yaml"
+    cases = [
+        dict(name="env1_seed1", cfg=env1, kw=dict(seed=1), steps=14),
+        dict(name="2turb_seed1", cfg=two, kw=dict(seed=1), steps=8),
+        dict(name="power_avg_yaw_dt2_total", kw=dict(seed=7, dt_env=2, dt_sim=1, yaw_step=2), steps=8,
+             cfg=small_config(2, 2, reward="Power_avg", action="yaw",
+                              **{"act_pen.action_penalty": 0.1, "act_pen.action_penalty_type": "Total"})),
+        dict(name="rich_3x1_global_base", kw=dict(seed=3, Baseline_comp=True), steps=8,
+             cfg=rich_config(3, 1, reward="Power_avg", BaseController="Global")),
+        dict(name="power_diff_change", kw=dict(seed=11), steps=6,
+             cfg=small_config(2, 1, reward="Power_diff", action="yaw",
+                              **{"power_def.Power_avg": 40, "act_pen.action_penalty": 0.02,
+                                 "ws_mes.ws_history_length": 45})),
+        dict(name="truncation_short", kw=dict(seed=5, n_passthrough=0.05), steps=8,
+             cfg=small_config(2, 1, reward="Power_avg", action="wind")),
+    ]
+    return cases
+
+
+def make_env(ns, out):
+    meta = {}
+    for c in env_cases(ns):
+        path = write_yaml(c["cfg"])
+        env = ns.WindFarmEnv(V80(), yaml_path=path, turbtype="None", **c["kw"])  # ctor resets with seed (:259-261)
+        obs0, info0 = env.reset(seed=c["kw"]["seed"])
+        T = env.n_turb
+        yaw0 = np.array(env.fs.windTurbines.yaw, dtype=np.float64).copy()
+        rng = np.random.default_rng(100 + c["kw"]["seed"])
+        acts = rng.uniform(-1, 1, (c["steps"], T)).astype(np.float32)
+        rec = {k: [] for k in ("obs", "reward", "trunc", "power", "yaw", "ws_turb", "wd_turb", "power_base",
+                               "yaw_base", "fs_time")}
+        for a in acts:
+            o, r, term, tr, info = env.step(a)
+            assert term is False
+            rec["obs"].append(o); rec["reward"].append(r); rec["trunc"].append(tr)
+            rec["power"].append(np.array(info["Power pr turbine agent"]))
+            rec["yaw"].append(np.array(info["yaw angles agent"]).copy())
+            rec["ws_turb"].append(np.array(info["Wind speed at turbines"]))
+            rec["wd_turb"].append(np.array(info["Wind direction at turbines"]))
+            rec["fs_time"].append(info.get("time_array", [np.nan])[-1] if False else np.nan)
+            if env.Baseline_comp:
+                rec["power_base"].append(np.array(info["Power pr turbine baseline"]))
+                rec["yaw_base"].append(np.array(info["yaw angles base"]).copy())
+            if tr:
+                break
+        n = len(rec["obs"])
+        pre = c["name"]
+        out[f"{pre}/acts"] = acts[:n]
+        out[f"{pre}/obs0"] = obs0
+        out[f"{pre}/yaw0"] = yaw0
+        for k, v in rec.items():
+            if k != "fs_time":
+                out[f"{pre}/{k}"] = np.array(v)
+        meta[pre] = dict(cfg=c["cfg"], kw=c["kw"], ws=float(env.ws) if n and not rec["trunc"][-1] else None,
+                         steps=n, n_turb=T)
+        # wind conditions / integers are read before a possible truncation teardown: re-create to read them safely
+        env2 = ns.WindFarmEnv(V80(), yaml_path=path, turbtype="None", **c["kw"])
+        env2.reset(seed=c["kw"]["seed"])
+        meta[pre].update(ws=float(env2.ws), ti=float(env2.ti), wd=float(env2.wd), time_max=int(env2.time_max),
+                         fs_time_after_reset=float(env2.fs.time), obs_var=int(env2.obs_var),
+                         rated_power=float(env2.rated_power))
+        os.unlink(path)
+
+    # FarmEval + ConstantAgent known answer (reference tests/test_basics.py:415-459 scenario)
+    path = write_yaml(ENV1)
+    fe = ns.FarmEvalCls(V80(), yaml_path=path, turbtype="None", yaw_init="Zeros", seed=2, reset_init=True)
+    fe.set_wind_vals(ws=10, ti=0.07, wd=270)
+    obs0, _ = fe.reset()
+    agent = ns.ConstantAgent(yaw_angles=[-10, 20, 0, 0])
+    yaws, powers = [np.array(fe.fs.windTurbines.yaw).copy()], []
+    obs = [obs0]
+    for _ in range(25):
+        a, _ = agent.predict(obs[-1])
+        o, r, te, tr, info = fe.step(a)
+        obs.append(o)
+        yaws.append(np.array(fe.fs.windTurbines.yaw).copy())
+        powers.append(np.array(fe.fs.windTurbines.power()))
+    out["farmeval/action"] = np.asarray(agent.predict()[0], dtype=np.float64)
+    out["farmeval/yaw"] = np.array(yaws)
+    out["farmeval/power"] = np.array(powers)
+    out["farmeval/obs"] = np.array(obs)
+    meta["farmeval"] = dict(fs_time_after_25=float(fe.fs.time), time_max=int(fe.time_max), ws=10, ti=0.07, wd=270)
+    os.unlink(path)
+    out["meta"] = np.array(json.dumps(meta))
+
+
+def main():
+    ns = load_reference()
+    mes, env = {}, {}
+    make_mes(ns, mes)
+    np.savez_compressed(os.path.join(HERE, "mes_golden.npz"), **mes)
+    make_env(ns, env)
+    np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **env)
+    for f in ("mes_golden.npz", "env_golden.npz"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,10 @@ struct wg_handle {
   size_t state_bytes = 0;
   int hist_max = 0;
   uint64_t launches = 0;
+  // optional per-kernel timing of wg_step (wg_profile_enable): event triples (before flow, after flow, after finish)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  size_t prof_used = 0;
   // device-resident immutable tables
   float *d_tab_ws = nullptr, *d_tab_p = nullptr, *d_tab_ct = nullptr;
   double *d_x = nullptr, *d_y = nullptr;
@@ -109,8 +113,6 @@ cudaError_t upload(Tp** dst, const Tp* src, size_t n) {
   if (e != cudaSuccess) return e;
   return cudaMemcpy(*dst, src, sizeof(Tp) * n, cudaMemcpyHostToDevice);
 }
-
-int chan_outputs(const wg_mes_channel& c, int gate) { return gate ? (c.current ? 1 : 0) + (c.rolling_mean ? c.history_N : 0) : 0; }
 
 // Observation descriptor list: order of farm_mes.get_measurements (MesClass.py:679-703) or, for the multi-agent
 // layout, of WindFarmEnvMulti._get_obs_multi (WindEnvMulti.py:79-103).
@@ -303,6 +305,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
 
 void wg_destroy(wg_handle* h) {
   if (!h) return;
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   cudaFree(h->d_tab_ws); cudaFree(h->d_tab_p); cudaFree(h->d_tab_ct); cudaFree(h->d_x); cudaFree(h->d_y);
   cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc);
   delete h;
@@ -396,13 +399,54 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   if (!h || !state || !actions || !obs || !reward || !truncated) return fail(WG_ERR_INVALID, "wg_step: null argument");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   wg::Dev d = bind(h, state);
+  cudaEvent_t* ev = nullptr;
+  if (h->profiling) {
+    if (h->prof_used + 3 > h->prof_events.size()) {
+      for (int i = 0; i < 3; ++i) {
+        cudaEvent_t e;
+        cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaEventCreate");
+        h->prof_events.push_back(e);
+      }
+    }
+    ev = &h->prof_events[h->prof_used];
+    h->prof_used += 3;
+    cudaEventRecord(ev[0], s);
+  }
   wg::FlowArgs fa{};
   fa.mode = wg::FLOW_STEP; fa.actions = actions; fa.farm_mask = (1 << d.F) - 1; fa.controller_on = 1;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
+  if (ev) cudaEventRecord(ev[1], s);
   wg::FinishArgs fin{};
   fin.flags = wg::FIN_PUSH_MES | wg::FIN_PUSH_FP | (d.F > 1 ? wg::FIN_PUSH_BP : 0) | wg::FIN_OBS | wg::FIN_REWARD;
   fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
   WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(step)");
+  if (ev) cudaEventRecord(ev[2], s);
+  return WG_OK;
+}
+
+int wg_profile_enable(wg_handle* h, int32_t on) {
+  if (!h) return fail(WG_ERR_INVALID, "wg_profile_enable: null argument");
+  h->profiling = on != 0;
+  h->prof_used = 0;
+  return WG_OK;
+}
+
+int wg_profile_read(wg_handle* h, double* flow_ms, double* finish_ms, uint64_t* n_steps) {
+  if (!h || !flow_ms || !finish_ms || !n_steps) return fail(WG_ERR_INVALID, "wg_profile_read: null argument");
+  double a = 0.0, b = 0.0;
+  const size_t n = h->prof_used / 3;
+  for (size_t i = 0; i < n; ++i) {
+    cudaEvent_t* ev = &h->prof_events[3 * i];
+    cudaError_t e = cudaEventSynchronize(ev[2]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+    float t0 = 0.f, t1 = 0.f;
+    if ((e = cudaEventElapsedTime(&t0, ev[0], ev[1])) != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+    if ((e = cudaEventElapsedTime(&t1, ev[1], ev[2])) != cudaSuccess) return cuda_fail(e, "cudaEventElapsedTime");
+    a += t0; b += t1;
+  }
+  *flow_ms = a; *finish_ms = b; *n_steps = n;
+  h->prof_used = 0;
   return WG_OK;
 }
 

@@ -137,6 +137,16 @@ class VecWindFarmEnv:
         _lib.check(self.lib.wg_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def profile_enable(self, on=True):
+        """Record CUDA events around the two kernels of every step() (measurement aid, see wg_profile_enable)."""
+        _lib.check(self.lib.wg_profile_enable(self._h, int(bool(on))))
+
+    def profile_read(self):
+        """(flow kernel ms, finish kernel ms, steps) summed over the recorded steps; synchronises."""
+        a, b, n = C.c_double(), C.c_double(), C.c_uint64()
+        _lib.check(self.lib.wg_profile_read(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     # ------------------------------------------------------------------------------------------ FarmEval surface
     def set_wind_vals(self, ws=None, ti=None, wd=None):
         """FarmEval.set_wind_vals (FarmEval.py:63-78); scalars or per-env arrays."""
