@@ -133,4 +133,8 @@ def test_flow_state_matches_oracle_particles(built_lib):
             assert np.allclose(pmut[:, :2], fs.pmut[t, sl, :2], atol=2e-2), "particle positions"
             assert np.abs(prof - fs.prof[t, sl]).max() < 2e-5, f"profiles max err {np.abs(prof - fs.prof[t, sl]).max():.2e}"
             assert np.allclose(pcon, fs.pcon[t, sl], atol=1e-4), "emission scalars"
+            U = fs.prof[t, sl]
+            M = np.sum((1.0 - U) * (np.arange(64) / 16.0)[None], axis=1) / 16.0
+            bw = np.sqrt(np.maximum(2.0 * M * (1.0 - U.min(axis=1)), 0.0))
+            assert np.allclose(env.last_bw, bw, atol=2e-5), "shear integral carried in the Dirichlet slot"
         assert np.allclose(env.state["u"][b, 0].cpu().numpy(), fs.rotor_avg_windspeed[:, 0], rtol=2e-5)

@@ -3,15 +3,25 @@
 //
 // One CTA owns one (env, farm).  Its live wake stations (all turbine chains, ring-addressed) form one flat
 // list that the CTA's warps stream in 32-station tiles:
-//     cp.async.bulk (TMA 1-D bulk copy, mbarrier complete_tx)  HBM -> shared,   double buffered per warp
-//     thread-per-station implicit Ainslie march (registers)                       r-stencil, Thomas solve
-//     rotor-plane bracket detection + deficit sampling of the freshly marched rows  (superposition gather)
+//     cp.async.bulk (TMA 1-D bulk copy, mbarrier complete_tx)  HBM -> shared
+//     thread-per-station implicit Ainslie march: ONE fused forward sweep (continuity-consistent radial
+//       velocity + tridiagonal rows + Thomas elimination; c' in registers, d' written in place into the
+//       shared row) and one back substitution that also accumulates the shear-layer integrals of the NEW
+//       profile for the next step's eddy viscosity
+//     rotor-plane bracket detection -> per-warp hit list -> (hit x quadrature point) mapped onto full warps,
+//       16-lane shuffle reduction for the rotor average                               (superposition gather)
 //     cp.async.bulk shared -> HBM
-// then the per-turbine epilogue (rotor average, P/CT tables, particle release) runs in the same CTA, and the
-// substep loop (dt_env/dt_sim, or a whole spin-up) repeats without leaving the kernel.
+// then the per-turbine epilogue (P/CT tables, particle release) runs in the same CTA, and the substep loop
+// (dt_env/dt_sim, or a whole spin-up) repeats without leaving the kernel.
 // Algorithmic traffic per station and step: 256 B profile + 16 B mutable + 16 B emission scalars read,
 // 256 B + 16 B written = 560 B.  HBM/issue bound; no tensor cores (stencil + gather).
+//
+// Profile row layout (64 floats, 16-byte chunks XOR-swizzled with slot & 7): nodes 0..62 hold U(r_j); node 63 is
+// the Dirichlet node (U = 1 always), so its slot carries bw = sqrt(2 M (1 - Umin)) of the row instead -- the
+// shear-layer term of the eddy viscosity (oracle/dwm_numpy.py:113-115), computed when the row was last written.
 #include <math_constants.h>
+
+#include <cstdlib>
 
 #include "wg_internal.cuh"
 
@@ -25,19 +35,28 @@ void set_rotor_points(const float* qy, const float* qz) {
   cudaMemcpyToSymbol(c_qz, qz, sizeof(float) * WG_NQ);
 }
 
+#define WG_NWARP 4        // warps per CTA
+#define WG_HIT_CAP 96     // per-warp hit list entries (flushed when fewer than 64 free)
+
 struct __align__(16) FlowShared {
-  unsigned long long mbar[8][2];
+  unsigned long long mbar[WG_NWARP][2];
   float xr[WG_MAX_T], yr[WG_MAX_T], yaw[WG_MAX_T], u[WG_MAX_T], v[WG_MAX_T], w[WG_MAX_T], pw[WG_MAX_T],
-      ct[WG_MAX_T], ind[WG_MAX_T];
+      ct[WG_MAX_T], ind[WG_MAX_T], bw0[WG_MAX_T];
+  float xs[WG_MAX_T];                       // turbine x sorted ascending
   float sum_ws[WG_MAX_T], sum_wd[WG_MAX_T], sum_yaw[WG_MAX_T], sum_pw[WG_MAX_T];
+  int ord[WG_MAX_T];                        // turbine index of xs[k]
   int head[WG_MAX_T], count[WG_MAX_T], pre[WG_MAX_T + 1], emit_slot[WG_MAX_T];
   float base_sum;
   int pad[3];
+  float4 hit_a[WG_NWARP][WG_HIT_CAP];       // w*U0e*cos g0, w*U0e*sin g0, ry, rz
+  int2 hit_b[WG_NWARP][WG_HIT_CAP];         // (row | key << 8), accumulator index j*T + chain
 };
 
-size_t flow_smem_bytes(int T, int n_warps) {
-  size_t acc = ((size_t)2 * T * T * sizeof(float) + 127) / 128 * 128;
-  return sizeof(FlowShared) + 128 + acc + (size_t)n_warps * 2 * WG_TILE * WG_ROW_BYTES;
+static size_t acc_bytes(int T) { return ((size_t)2 * T * T * sizeof(float) + 127) / 128 * 128; }
+static size_t hdr_bytes() { return (sizeof(FlowShared) + 127) / 128 * 128; }
+
+size_t flow_smem_bytes(int T, int n_stage) {
+  return hdr_bytes() + acc_bytes(T) + (size_t)WG_NWARP * n_stage * WG_TILE * WG_ROW_BYTES;
 }
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -84,6 +103,11 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 // ---------------------------------------------------------------------------------------------- physics
 __device__ __forceinline__ float f1_filter(float xt) {
@@ -124,96 +148,101 @@ __device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws
   zn = pm.z;
 }
 
-// Implicit Ainslie march of one profile row held in shared memory (chunk-swizzled with `key`).
-// Registers: u[64] (profile -> rhs -> solution) and vh[64] (radial velocity per unit nu -> Thomas c').
+__device__ __forceinline__ float4 ld_chunk(const float* row, int key, int c) {
+  return *reinterpret_cast<const float4*>(row + ((c ^ key) << 2));
+}
+__device__ __forceinline__ void st_chunk(float* row, int key, int c, float4 v) {
+  *reinterpret_cast<float4*>(row + ((c ^ key) << 2)) = v;
+}
+
+// Implicit Ainslie march of one profile row held in shared memory (oracle/dwm_numpy.py:ainslie_march).
+// Forward sweep: per node j the continuity-consistent radial velocity (pass A of the oracle) feeds the
+// tridiagonal row and its Thomas elimination (pass B) immediately; the eddy viscosity needs the row's shear
+// integral bw, which rides in slot 63.  c' stays in registers, d' replaces U_j in the shared row.
+// Back substitution (pass C) writes the new profile and accumulates its bw.  Returns the new centre value.
 __device__ __forceinline__ float march_row(float* __restrict__ row, int key, float dxt, float xt, float knu1) {
-  float u[WG_NR], vh[WG_NR];
-#pragma unroll
-  for (int c = 0; c < WG_NR / 4; ++c) {
-    float4 t = *reinterpret_cast<const float4*>(row + ((c ^ key) << 2));
-    u[4 * c + 0] = t.x; u[4 * c + 1] = t.y; u[4 * c + 2] = t.z; u[4 * c + 3] = t.w;
-  }
   constexpr float IDR2 = 1.f / (DR * DR);
   constexpr float HDR = 0.5f * DR;
   constexpr float I2DR = 0.5f / DR;
-  // ---- pass A: Laplacian, continuity-consistent radial velocity per unit nu, integrals for nu
-  float I = 0.f, rgp = 0.f, M = 0.f, umin = u[0];
-#pragma unroll
-  for (int j = 1; j < WG_NR - 1; ++j) {
-    const float r = j * DR, rinv = 1.f / r;
-    float up = (u[j + 1] - u[j - 1]) * I2DR;
-    float upr = up * rinv;
-    float lap = fmaf(fmaf(-2.f, u[j], u[j + 1] + u[j - 1]), IDR2, upr);
-    float Ip = fmaf(HDR, rgp, I);
-    float den = fmaf(-HDR, up, u[j]);
-    float g = fmaf(upr, Ip, lap) * rcp_fast(den);
-    float rg = r * g;
-    I = fmaf(HDR, rg, Ip);
-    vh[j] = -I * rinv;
-    rgp = rg;
-    M = fmaf(r, 1.f - u[j], M);
-    umin = fminf(umin, u[j]);
-  }
-  umin = fminf(umin, u[WG_NR - 1]);
-  const float lap0 = 4.f * (u[1] - u[0]) * IDR2;
-  (void)lap0;
-  M *= DR;
-  const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * sqrtf(fmaxf(2.f * M * (1.f - umin), 0.f));
-  // ---- pass B: tridiagonal rows + Thomas forward sweep (unknowns 0..62, u[63] = 1 Dirichlet)
+  float cp[WG_NR - 1];
+  float4 cur = ld_chunk(row, key, 0);
+  const float bw = ld_chunk(row, key, WG_NR / 4 - 1).w;
+  const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
   const float idx = 1.f / fmaxf(dxt, DXT_MIN);
   const float nu2 = 2.f * nu * IDR2, nu8 = nu * I2DR;
-  float cpm, dpm;
-  {
-    float m = rcp_fast(fmaf(u[0], idx, 2.f * nu2));
-    cpm = -2.f * nu2 * m;
-    dpm = u[0] * u[0] * idx * m;
-    vh[0] = cpm;
-    u[0] = dpm;
-  }
-#pragma unroll
-  for (int j = 1; j < WG_NR - 1; ++j) {
-    const float rinv = 1.f / (j * DR);
-    const float am = (1.f - HDR * rinv) * IDR2, ap = (1.f + HDR * rinv) * IDR2;
-    float Vd = nu8 * vh[j];
-    float a = -fmaf(nu, am, Vd);
-    float c = fmaf(-nu, ap, Vd);
-    float bb = fmaf(u[j], idx, nu2);
-    float dd = u[j] * u[j] * idx;
-    if (j == WG_NR - 2) dd -= c;
-    float m = rcp_fast(fmaf(-a, cpm, bb));
-    cpm = c * m;
-    dpm = fmaf(-a, dpm, dd) * m;
-    vh[j] = cpm;
-    u[j] = dpm;
-  }
-  // ---- pass C: back substitution
-  u[WG_NR - 1] = 1.f;
-#pragma unroll
-  for (int j = WG_NR - 3; j >= 0; --j) u[j] = fmaf(-vh[j], u[j + 1], u[j]);
+  float I = 0.f, rgp = 0.f, cpm, dpm;
+  float um = 0.f;  // U_{j-1}
 #pragma unroll
   for (int c = 0; c < WG_NR / 4; ++c) {
-    float4 t = make_float4(u[4 * c + 0], u[4 * c + 1], u[4 * c + 2], u[4 * c + 3]);
-    *reinterpret_cast<float4*>(row + ((c ^ key) << 2)) = t;
+    float4 nxt = cur;
+    if (c + 1 < WG_NR / 4) nxt = ld_chunk(row, key, c + 1);
+    if (c + 1 == WG_NR / 4 - 1) nxt.w = 1.f;  // Dirichlet node: the slot holds bw, the value is 1
+    const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+    float dout[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int j = 4 * c + e;
+      const float uj = uu[e], up1 = uu[e + 1];
+      if (j == 0) {
+        const float m = rcp_fast(fmaf(uj, idx, 2.f * nu2));
+        cpm = -2.f * nu2 * m;
+        dpm = uj * uj * idx * m;
+        cp[0] = cpm;
+        dout[e] = dpm;
+      } else if (j < WG_NR - 1) {
+        const float r = j * DR, rinv = 1.f / r;
+        const float am = (1.f - HDR * rinv) * IDR2, ap = (1.f + HDR * rinv) * IDR2;
+        const float up = (up1 - um) * I2DR;
+        const float upr = up * rinv;
+        const float lap = fmaf(fmaf(-2.f, uj, up1 + um), IDR2, upr);
+        const float Ip = fmaf(HDR, rgp, I);
+        const float den = fmaf(-HDR, up, uj);
+        const float g = fmaf(upr, Ip, lap) * rcp_fast(den);
+        const float rg = r * g;
+        I = fmaf(HDR, rg, Ip);
+        rgp = rg;
+        const float Vd = -nu8 * rinv * I;        // nu * Vh_j / (2 dr)
+        const float a = fmaf(nu, am, Vd);        // -(sub-diagonal)
+        const float cc = fmaf(-nu, ap, Vd);      // super-diagonal
+        const float bb = fmaf(uj, idx, nu2);
+        float dd = uj * uj * idx;
+        if (j == WG_NR - 2) dd -= cc;            // Dirichlet U_63 = 1
+        const float m = rcp_fast(fmaf(a, cpm, bb));
+        cpm = cc * m;
+        dpm = fmaf(a, dpm, dd) * m;
+        cp[j] = cpm;
+        dout[e] = dpm;
+      } else {
+        dout[e] = 0.f;
+      }
+      um = uj;
+    }
+    if (c < WG_NR / 4 - 1) st_chunk(row, key, c, make_float4(dout[0], dout[1], dout[2], dout[3]));
+    else cur = make_float4(dout[0], dout[1], dout[2], 0.f);  // last chunk stays in registers: d'_60..62
+    if (c < WG_NR / 4 - 1) cur = nxt;
   }
-  return u[0];
-}
-
-// rotor-averaged deficit of one marched row for a rotor whose centre sits (ry, rz) rotor radii off the wake centre
-__device__ __forceinline__ float rotor_deficit(const float* __restrict__ row, int key, float ry, float rz) {
-  float acc = 0.f;
-#pragma unroll 4
-  for (int q = 0; q < WG_NQ; ++q) {
-    float dy = ry + c_qy[q], dz = rz + c_qz[q];
-    float s = sqrtf(dy * dy + dz * dz) * (1.f / DR);
-    int j0 = min((int)s, WG_NR - 2);
-    float fr = s - (float)j0;
-    int j1 = j0 + 1;
-    float u0 = row[(((j0 >> 2) ^ key) << 2) | (j0 & 3)];
-    float u1 = row[(((j1 >> 2) ^ key) << 2) | (j1 & 3)];
-    float d = (1.f - u0) * (1.f - fr) + (1.f - u1) * fr;
-    acc += (s >= (float)(WG_NR - 1)) ? 0.f : d;
+  // ---- back substitution + shear integrals of the new profile
+  float un = 1.f, M = 0.f, umin = 1.f;
+#pragma unroll
+  for (int c = WG_NR / 4 - 1; c >= 0; --c) {
+    float4 dq = (c == WG_NR / 4 - 1) ? cur : ld_chunk(row, key, c);
+    float dv[4] = {dq.x, dq.y, dq.z, dq.w};
+    float o[4];
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+      const int j = 4 * c + e;
+      if (j == WG_NR - 1) { o[e] = 0.f; continue; }
+      un = (j == WG_NR - 2) ? dv[e] : fmaf(-cp[j], un, dv[e]);
+      o[e] = un;
+      M = fmaf(j * DR, 1.f - un, M);
+      umin = fminf(umin, un);
+    }
+    if (c < WG_NR / 4 - 1) st_chunk(row, key, c, make_float4(o[0], o[1], o[2], o[3]));
+    else cur = make_float4(o[0], o[1], o[2], 0.f);
   }
-  return acc * (1.f / WG_NQ);
+  cur.w = sqrtf(fmaxf(2.f * (M * DR) * (1.f - umin), 0.f));
+  st_chunk(row, key, WG_NR / 4 - 1, cur);
+  return un;
 }
 
 struct LaneLoc {
@@ -255,7 +284,44 @@ __device__ __forceinline__ Seg segments(const LaneLoc& L, int lane) {
   return s;
 }
 
-__global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
+// Evaluate the queued (station row, rotor) hits of one warp: two hits per pass, 16 quadrature points each on
+// 16 lanes, shuffle-reduced to the rotor average, accumulated per (rotor, emitting chain).
+__device__ __forceinline__ void flush_hits(const float* __restrict__ tile, const float4* __restrict__ ha,
+                                           const int2* __restrict__ hb, int nh, float* acc_du, float* acc_dv,
+                                           int lane, float qy, float qz) {
+  const unsigned full = 0xffffffffu;
+  const int half = lane >> 4;
+  for (int h0 = 0; h0 < nh; h0 += 2) {
+    const int h = h0 + half;
+    const bool ok = h < nh;
+    const float4 a = ha[ok ? h : h0];
+    const int2 b = hb[ok ? h : h0];
+    const float* row = tile + (b.x & 0xff) * WG_NR;
+    const int key = b.x >> 8;
+    const float dy = a.z + qy, dz = a.w + qz;
+    const float s = sqrt_fast(fmaf(dy, dy, dz * dz)) * (1.f / DR);
+    const int j0 = min((int)s, WG_NR - 2);
+    const float fr = s - (float)j0;
+    const int j1 = j0 + 1;
+    const float u0 = row[(((j0 >> 2) ^ key) << 2) | (j0 & 3)];
+    float u1 = row[(((j1 >> 2) ^ key) << 2) | (j1 & 3)];
+    if (j1 == WG_NR - 1) u1 = 1.f;
+    float d = fmaf(fr, u0 - u1, 1.f - u0);  // (1-u0)(1-fr) + (1-u1) fr
+    if (s >= (float)(WG_NR - 1) || !ok) d = 0.f;
+    d += __shfl_xor_sync(full, d, 8);
+    d += __shfl_xor_sync(full, d, 4);
+    d += __shfl_xor_sync(full, d, 2);
+    d += __shfl_xor_sync(full, d, 1);
+    if ((lane & 15) == 0 && ok) {
+      d *= (1.f / WG_NQ);
+      atomicAdd(&acc_du[b.y], a.x * d);
+      atomicAdd(&acc_dv[b.y], a.y * d);
+    }
+  }
+}
+
+template <int NSTAGE>
+__global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FlowShared& sh = *reinterpret_cast<FlowShared*>(smem_raw);
   const int T = d.T, P = d.P, F = d.F;
@@ -264,7 +330,7 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
   float* bufs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(acc_du) +
                                          (((size_t)2 * T * T * sizeof(float) + 127) / 128) * 128);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = blockDim.x >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / F, f = blockIdx.x % F;
   const int bf = b * F + f;
   if (a.mask && !a.mask[b]) return;
@@ -273,6 +339,7 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
   if (nsteps <= 0) return;
 
   const float ws = d.ws[b], wd = d.wd[b], dt = d.dt, R = d.R, xmax = d.xmax[b];
+  const float rR = 1.f / R;
   const float ti = d.ti[b];
   const float knu1_env = ti > 0.f ? K1 * powf(ti, 0.3f) : 0.f;
   const int k_emit = max(d.k_emit[b], 1);
@@ -280,7 +347,8 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
   float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;
   float* pmut0 = d.pmut + (size_t)bf * T * P * 4;
   float* pmut1 = pmut0 + (size_t)d.B * F * T * P * 4;
-  float* my_buf = bufs + (size_t)warp * 2 * WG_TILE * WG_NR;
+  float* my_buf = bufs + (size_t)warp * NSTAGE * WG_TILE * WG_NR;
+  const float qy = c_qy[lane & 15], qz = c_qz[lane & 15];
 
   if (tid < T) {
     sh.xr[tid] = d.xr[b * T + tid];
@@ -315,6 +383,17 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
   }
   int nstep = d.n_step[bf];
   uint32_t phase = 0;
+  __syncthreads();
+  if (tid < T) {  // rank sort of the rotor-plane x positions (ties broken by index): xs ascending, ord = turbine
+    const float x = sh.xr[tid];
+    int rank = 0;
+    for (int t = 0; t < T; ++t) {
+      const float xt = sh.xr[t];
+      rank += (xt < x || (xt == x && t < tid)) ? 1 : 0;
+    }
+    sh.xs[rank] = x;
+    sh.ord[rank] = tid;
+  }
   __syncthreads();
 
   for (int sub = 0; sub < nsteps; ++sub) {
@@ -365,7 +444,7 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
     float4 pmc, pcc, pmn, pcn;
     int stage = 0;
     Lc.valid = 0; Lc.chain = 0; Lc.slot = 0; Lc.q = 0;
-    pmc = pcc = make_float4(0.f, 0.f, 0.f, 0.f);
+    pmc = pcc = pmn = pcn = make_float4(0.f, 0.f, 0.f, 0.f);
     auto issue_load = [&](const LaneLoc& L, int stg) {
       Seg sg = segments(L, lane);
       void* bar = &sh.mbar[warp][stg];
@@ -386,26 +465,27 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
       issue_load(Lc, 0);
       load_scalars(Lc, pmc, pcc);
     }
-    for (int tile = warp; tile < ntiles; tile += NW) {
-      const int nt = tile + NW;
-      bulk_wait_read0();  // stores that used the other stage have drained their shared-memory reads
-      __syncwarp();
+    for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
+      const int nt = tile + WG_NWARP;
       Ln.valid = 0;
-      if (nt < ntiles) {
-        Ln = locate(sh, nt, lane, T, P, ntot);
-        issue_load(Ln, stage ^ 1);
-        load_scalars(Ln, pmn, pcn);
+      if (nt < ntiles) Ln = locate(sh, nt, lane, T, P, ntot);
+      if (NSTAGE == 2) {
+        bulk_wait_read0();  // stores that used the other stage have drained their shared-memory reads
+        __syncwarp();
+        if (nt < ntiles) issue_load(Ln, stage ^ 1);
       }
+      if (nt < ntiles) load_scalars(Ln, pmn, pcn);
       mbar_wait(&sh.mbar[warp][stage], (phase >> stage) & 1u);
       phase ^= (1u << stage);
 
-      float* row = my_buf + ((size_t)stage * WG_TILE + lane) * WG_NR;
+      float* tile_base = my_buf + (size_t)stage * WG_TILE * WG_NR;
+      float* row = tile_base + lane * WG_NR;
       const int key = Lc.slot & 7;
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
       if (Lc.valid) {
         moved(pmc, pcc, ws, dt, xn, yn, zn, dx);
-        float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) / R;
-        float ucn = march_row(row, key, dx / R, xt_mid, pcc.y);
+        float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
+        float ucn = march_row(row, key, dx * rR, xt_mid, pcc.y);
         *reinterpret_cast<float4*>(pm_new + ((size_t)Lc.chain * P + Lc.slot) * 4) = make_float4(xn, yn, zn, ucn);
       }
       fence_async_smem();
@@ -426,8 +506,8 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
         int cy = __shfl_down_sync(full, Lc.chain, 1);
         int vy_ = __shfl_down_sync(full, Lc.valid, 1);
-        bool has_o = Lc.valid && Lc.q > 0;
-        bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
+        const bool has_o = Lc.valid && Lc.q > 0;
+        const bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
         if (has_o && (lane == 0 || co != Lc.chain)) {
           int so = Lc.slot == 0 ? P - 1 : Lc.slot - 1;
           float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + so) * 4));
@@ -442,7 +522,7 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
           float dxx;
           moved(pm, pc, ws, dt, xy, yy, zy, dxx);
         }
-        // x-range touched by this tile (warp-uniform early-out per turbine)
+        // x-range touched by this tile (warp-uniform): only rotor planes inside it can be bracketed
         float lo = Lc.valid ? xn : CUDART_INF_F, hi = Lc.valid ? xn : -CUDART_INF_F;
         if (has_o) { lo = fminf(lo, xo); hi = fmaxf(hi, xo); }
         if (has_y) { lo = fminf(lo, xy); hi = fmaxf(hi, xy); }
@@ -452,43 +532,61 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
           hi = fmaxf(hi, __shfl_xor_sync(full, hi, o));
         }
         const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
-        for (int j = 0; j < T; ++j) {
-          const float xj = sh.xr[j];
-          if (xj < lo || xj >= hi) continue;
-          if (!Lc.valid || j == Lc.chain) continue;
-          float wsum_du = 0.f;  // signed interpolation weight * rotor-mean deficit, both intervals
-          bool any = false;
-          float wgt[2], ycs[2], zcs[2];
-          int nh = 0;
-          if (has_o) {  // interval (self = younger end, older neighbour)
-            float sgn = (xn <= xj && xj < xo) ? 1.f : ((xo <= xj && xj < xn) ? -1.f : 0.f);
-            if (sgn != 0.f) {
-              float w = (xj - xn) / (xo - xn);
-              wgt[nh] = sgn * (1.f - w); ycs[nh] = yn * (1.f - w) + yo * w; zcs[nh] = zn * (1.f - w) + zo * w;
-              ++nh;
-            }
+        float4* ha = sh.hit_a[warp];
+        int2* hb = sh.hit_b[warp];
+        const unsigned lt = (1u << lane) - 1u;
+        const int rowkey = lane | (key << 8);
+        int nh = 0;
+        int k = 0;
+        while (k < T && sh.xs[k] < lo) ++k;
+        for (; k < T; ++k) {
+          const float xj = sh.xs[k];
+          if (xj >= hi) break;
+          const int j = sh.ord[k];
+          const bool mine = Lc.valid && j != Lc.chain;
+          // interval A: (self = younger end, older neighbour); interval B: (younger neighbour, self = older end)
+          float sgA = 0.f, sgB = 0.f;
+          if (mine && has_o) sgA = (xn <= xj && xj < xo) ? 1.f : ((xo <= xj && xj < xn) ? -1.f : 0.f);
+          if (mine && has_y) sgB = (xy <= xj && xj < xn) ? 1.f : ((xn <= xj && xj < xy) ? -1.f : 0.f);
+          const unsigned mA = __ballot_sync(full, sgA != 0.f), mB = __ballot_sync(full, sgB != 0.f);
+          if ((mA | mB) == 0u) continue;
+          const float yrj = sh.yr[j];
+          if (sgA != 0.f) {
+            const float w = (xj - xn) / (xo - xn);
+            const float wg = sgA * (1.f - w);
+            const float yc = yn * (1.f - w) + yo * w, zc = zn * (1.f - w) + zo * w;
+            const int p = nh + __popc(mA & lt);
+            ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
+            hb[p] = make_int2(rowkey, j * T + Lc.chain);
           }
-          if (has_y) {  // interval (younger neighbour, self = older end)
-            float sgn = (xy <= xj && xj < xn) ? 1.f : ((xn <= xj && xj < xy) ? -1.f : 0.f);
-            if (sgn != 0.f) {
-              float w = (xj - xy) / (xn - xy);
-              wgt[nh] = sgn * w; ycs[nh] = yy * (1.f - w) + yn * w; zcs[nh] = zy * (1.f - w) + zn * w;
-              ++nh;
-            }
+          nh += __popc(mA);
+          if (sgB != 0.f) {
+            const float w = (xj - xy) / (xn - xy);
+            const float wg = sgB * w;
+            const float yc = yy * (1.f - w) + yn * w, zc = zy * (1.f - w) + zn * w;
+            const int p = nh + __popc(mB & lt);
+            ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
+            hb[p] = make_int2(rowkey, j * T + Lc.chain);
           }
-          for (int h = 0; h < nh; ++h) {
-            float Dq = rotor_deficit(row, key, (sh.yr[j] - ycs[h]) / R, (d.zh - zcs[h]) / R);
-            wsum_du += wgt[h] * Dq;
-            any = true;
-          }
-          if (any) {
-            atomicAdd(&acc_du[j * T + Lc.chain], wsum_du * u0cg);
-            atomicAdd(&acc_dv[j * T + Lc.chain], wsum_du * u0sg);
+          nh += __popc(mB);
+          if (nh > WG_HIT_CAP - 64) {
+            __syncwarp();
+            flush_hits(tile_base, ha, hb, nh, acc_du, acc_dv, lane, qy, qz);
+            __syncwarp();
+            nh = 0;
           }
         }
+        __syncwarp();
+        flush_hits(tile_base, ha, hb, nh, acc_du, acc_dv, lane, qy, qz);
       }
       __syncwarp();
-      stage ^= 1;
+      if (NSTAGE == 1) {
+        bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
+        __syncwarp();
+        if (nt < ntiles) issue_load(Ln, 0);
+      } else {
+        stage ^= 1;
+      }
       Lc = Ln; pmc = pmn; pcc = pcn;
     }
     bulk_wait_all0();
@@ -516,12 +614,21 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
         slot = sh.head[tid];
         if (sh.count[tid] == P) atomicOr(&d.flags[b], 2); else sh.count[tid] += 1;
         sh.head[tid] = (slot + 1 == P) ? 0 : slot + 1;
-        // inlet value at the centre node (cell [0, dr/2]) -- same formula as the row writer below
+        // cell-averaged top-hat inlet (same formula as the row writer below): centre value and shear integral
         const float fw = 1.f - 0.45f * ind * ind;
         const float rw2 = fw * fw * (1.f - ind) / (1.f - 2.f * ind);
-        const float frac0 = fminf(fmaxf(rw2 / (0.25f * DR * DR), 0.f), 1.f);
+        float M = 0.f, u0v = 1.f;
+        for (int j = 0; j < WG_NR - 1; ++j) {
+          const float rlo = fmaxf((float)j - 0.5f, 0.f) * DR, rhi = ((float)j + 0.5f) * DR;
+          const float frac = fminf(fmaxf((rw2 - rlo * rlo) / (rhi * rhi - rlo * rlo), 0.f), 1.f);
+          const float df = 2.f * ind * frac;
+          if (j == 0) u0v = 1.f - df;
+          M = fmaf((float)j * DR, df, M);
+        }
+        // the inlet is monotone non-decreasing in r, so Umin is the centre value
+        sh.bw0[tid] = sqrtf(fmaxf(2.f * (M * DR) * (1.f - u0v), 0.f));
         *reinterpret_cast<float4*>(pm_new + ((size_t)tid * P + slot) * 4) =
-            make_float4(sh.xr[tid], sh.yr[tid], d.zh, 1.f - 2.f * ind * frac0);
+            make_float4(sh.xr[tid], sh.yr[tid], d.zh, u0v);
         *reinterpret_cast<float4*>(pcon + ((size_t)tid * P + slot) * 4) = make_float4(u, knu1_env, cg, sg);
       }
       sh.emit_slot[tid] = slot;
@@ -554,7 +661,7 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
           const int j = 4 * c + e;
           const float rlo = fmaxf((float)j - 0.5f, 0.f) * DR, rhi = ((float)j + 0.5f) * DR;
           const float frac = fminf(fmaxf((rw2 - rlo * rlo) / (rhi * rhi - rlo * rlo), 0.f), 1.f);
-          vals[e] = (j == WG_NR - 1) ? 1.f : 1.f - 2.f * ind * frac;
+          vals[e] = (j == WG_NR - 1) ? sh.bw0[t] : 1.f - 2.f * ind * frac;
         }
         *reinterpret_cast<float4*>(prof + ((size_t)t * P + slot) * WG_NR + ((c ^ (slot & 7)) << 2)) =
             make_float4(vals[0], vals[1], vals[2], vals[3]);
@@ -588,16 +695,30 @@ __global__ void __launch_bounds__(128, 3) wg_flow_kernel(const Dev d, const Flow
   }
 }
 
-cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  const int n_warps = 4;
-  const size_t smem = flow_smem_bytes(d.T, n_warps);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(wg_flow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
+// Tile buffers per warp: 1 (default; 4 CTAs/SM, latency hidden by the other warps) or 2 (WG_FLOW_STAGES=2; the next
+// tile is prefetched while the current one is marched, 3 CTAs/SM).
+static int flow_stages() {
+  static int n = 0;
+  if (n == 0) {
+    const char* e = getenv("WG_FLOW_STAGES");
+    n = (e && e[0] == '2') ? 2 : 1;
   }
-  wg_flow_kernel<<<d.B * d.F, n_warps * 32, smem, s>>>(d, a);
+  return n;
+}
+
+cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
+  const int ns = flow_stages();
+  const size_t smem = flow_smem_bytes(d.T, ns);
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > configured[ns]) {
+    cudaError_t e = ns == 1
+        ? cudaFuncSetAttribute(wg_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(wg_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured[ns] = smem;
+  }
+  if (ns == 1) wg_flow_kernel<1><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  else wg_flow_kernel<2><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
 

@@ -282,6 +282,9 @@ class VecWindFarmEnv:
         key = (slots & 7)[:, None]
         idx = np.arange(16)[None, :] ^ key
         prof = np.take_along_axis(raw, idx[:, :, None], axis=1).reshape(cnt, 64)
+        # node 63 is the Dirichlet node (U = 1); its slot carries the row's shear integral sqrt(2 M (1 - Umin))
+        self.last_bw = prof[:, 63].copy()
+        prof[:, 63] = 1.0
         pmut = s["pmut"][par, b, f, t].cpu().numpy()[slots]
         pcon = s["pcon"][b, f, t].cpu().numpy()[slots]
         return prof, pmut, pcon
