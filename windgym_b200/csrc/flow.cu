@@ -30,33 +30,42 @@ namespace wg {
 __constant__ float c_qy[WG_NQ];
 __constant__ float c_qz[WG_NQ];
 
-void set_rotor_points(const float* qy, const float* qz) {
-  cudaMemcpyToSymbol(c_qy, qy, sizeof(float) * WG_NQ);
-  cudaMemcpyToSymbol(c_qz, qz, sizeof(float) * WG_NQ);
-}
 
 #define WG_NWARP 4        // warps per CTA
 #define WG_HIT_CAP 96     // per-warp hit list entries (flushed when fewer than 64 free)
 
+// per-node constants of the radial grid r_j = j dr: {1/(2j), j/2}; entry 0 unused (the axis node has its own row)
+__constant__ float2 c_node[WG_NR];
+
+void set_rotor_points(const float* qy, const float* qz) {
+  cudaMemcpyToSymbol(c_qy, qy, sizeof(float) * WG_NQ);
+  cudaMemcpyToSymbol(c_qz, qz, sizeof(float) * WG_NQ);
+  float2 nd[WG_NR];
+  nd[0] = make_float2(0.f, 0.f);
+  for (int j = 1; j < WG_NR; ++j) nd[j] = make_float2(1.f / (2.f * j), 0.5f * j);
+  cudaMemcpyToSymbol(c_node, nd, sizeof(nd));
+}
+
 struct __align__(16) FlowShared {
-  unsigned long long mbar[WG_NWARP][2];
+  unsigned long long mbar[WG_NWARP];
   float xr[WG_MAX_T], yr[WG_MAX_T], yaw[WG_MAX_T], u[WG_MAX_T], v[WG_MAX_T], w[WG_MAX_T], pw[WG_MAX_T],
-      ct[WG_MAX_T], ind[WG_MAX_T], bw0[WG_MAX_T];
+      ct[WG_MAX_T], ind[WG_MAX_T], cg[WG_MAX_T], sg[WG_MAX_T];
   float xs[WG_MAX_T];                       // turbine x sorted ascending
   float sum_ws[WG_MAX_T], sum_wd[WG_MAX_T], sum_yaw[WG_MAX_T], sum_pw[WG_MAX_T];
+  float acc_du[WG_NWARP][WG_MAX_T], acc_dv[WG_NWARP][WG_MAX_T];  // per-warp superposed deficit per rotor
   int ord[WG_MAX_T];                        // turbine index of xs[k]
   int head[WG_MAX_T], count[WG_MAX_T], pre[WG_MAX_T + 1], emit_slot[WG_MAX_T];
   float base_sum;
   int pad[3];
   float4 hit_a[WG_NWARP][WG_HIT_CAP];       // w*U0e*cos g0, w*U0e*sin g0, ry, rz
-  int2 hit_b[WG_NWARP][WG_HIT_CAP];         // (row | key << 8), accumulator index j*T + chain
+  int2 hit_b[WG_NWARP][WG_HIT_CAP];         // (row | key << 8), rotor index j
 };
 
-static size_t acc_bytes(int T) { return ((size_t)2 * T * T * sizeof(float) + 127) / 128 * 128; }
 static size_t hdr_bytes() { return (sizeof(FlowShared) + 127) / 128 * 128; }
 
 size_t flow_smem_bytes(int T, int n_stage) {
-  return hdr_bytes() + acc_bytes(T) + (size_t)WG_NWARP * n_stage * WG_TILE * WG_ROW_BYTES;
+  (void)T;
+  return hdr_bytes() + (size_t)WG_NWARP * n_stage * WG_TILE * WG_ROW_BYTES;
 }
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
@@ -114,7 +123,7 @@ __device__ __forceinline__ float f1_filter(float xt) {
   if (xt >= 8.f) return 1.f;
   float q = fmaxf(xt, 0.f) * 0.125f;
   float s = q * sqrtf(q);
-  return s - sinf(6.283185307179586f * s) * 0.15915494309189535f;
+  return s - __sinf(6.283185307179586f * s) * 0.15915494309189535f;  // argument in [0, 2 pi]
 }
 __device__ __forceinline__ float f2_filter(float xt) {
   float lin = 0.025f * xt - 0.0375f;
@@ -160,18 +169,47 @@ __device__ __forceinline__ void st_chunk(float* row, int key, int c, float4 v) {
 // tridiagonal row and its Thomas elimination (pass B) immediately; the eddy viscosity needs the row's shear
 // integral bw, which rides in slot 63.  c' stays in registers, d' replaces U_j in the shared row.
 // Back substitution (pass C) writes the new profile and accumulates its bw.  Returns the new centre value.
-__device__ __forceinline__ float march_row(float* __restrict__ row, int key, float dxt, float xt, float knu1) {
+// Both sweeps are rolled over eight 8-node groups of the row (per-node grid constants come from c_node)
+// so that the loop body stays inside the instruction cache; within a group everything is unrolled and c' is
+// statically indexed.  With h = 1/(2j), N = nu/dr^2:
+//   lap_j dr^2 = U_{j+1} + U_{j-1} - 2 U_j + h (U_{j+1} - U_{j-1}),  Vd_j = nu Vh_j / (2 dr) = -N h I_j,
+//   sub-diagonal -a_j = -(N - N h (1 + I_j)), super-diagonal c_j = -N - N h (1 + I_j), diagonal U_j/dx + 2N.
+// Node j of the forward sweep (shared by both march variants).  nd = {1/(2j), j/2}.
+#define WG_NODE_FWD(uj, up1, um, nd, AXIS)                                              \
+  {                                                                                     \
+    const float ui = (uj) * idx;                                                        \
+    float bb = ui + N2, dd = ui * (uj), a = 0.f, cc = -2.f * N2;                        \
+    if (AXIS) {                                                                         \
+      bb += N2; /* axis node: diagonal U_0/dx + 4N, super-diagonal -4N, no sub-diagonal */ \
+    } else {                                                                            \
+      const float du = (up1) - (um), su = (up1) + (um);                                 \
+      const float hd = (nd).x * du;                                                     \
+      const float t2 = fmaf(-2.f, (uj), hd + su);                                       \
+      const float Ip = I + rgh;                                                         \
+      const float den = fmaf(-0.25f, du, (uj));                                         \
+      const float G = fmaf(hd, Ip, t2) * rcp_fast(den);                                 \
+      rgh = (nd).y * G;                                                                 \
+      I = Ip + rgh;                                                                     \
+      const float nh = N * (nd).x;                                                      \
+      const float t = fmaf(-nh, I, -nh);                                                \
+      a = t + N;                                                                        \
+      cc = t - N;                                                                       \
+    }                                                                                   \
+    const float m = rcp_fast(fmaf(a, cpm, bb));                                         \
+    cpm = cc * m;                                                                       \
+    dpm = fmaf(a, dpm, dd) * m;                                                         \
+  }
+
+// Variant 0: everything unrolled, c' in 63 registers (grid constants become immediates).
+__device__ __forceinline__ float march_row_regs(float* __restrict__ row, int key, float dxt, float xt, float knu1) {
   constexpr float IDR2 = 1.f / (DR * DR);
-  constexpr float HDR = 0.5f * DR;
-  constexpr float I2DR = 0.5f / DR;
-  float cp[WG_NR - 1];
+  float cp[WG_NR];
   float4 cur = ld_chunk(row, key, 0);
   const float bw = ld_chunk(row, key, WG_NR / 4 - 1).w;
   const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
   const float idx = 1.f / fmaxf(dxt, DXT_MIN);
-  const float nu2 = 2.f * nu * IDR2, nu8 = nu * I2DR;
-  float I = 0.f, rgp = 0.f, cpm, dpm;
-  float um = 0.f;  // U_{j-1}
+  const float N = nu * IDR2, N2 = 2.f * N;
+  float I = 0.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
 #pragma unroll
   for (int c = 0; c < WG_NR / 4; ++c) {
     float4 nxt = cur;
@@ -182,66 +220,91 @@ __device__ __forceinline__ float march_row(float* __restrict__ row, int key, flo
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int j = 4 * c + e;
-      const float uj = uu[e], up1 = uu[e + 1];
-      if (j == 0) {
-        const float m = rcp_fast(fmaf(uj, idx, 2.f * nu2));
-        cpm = -2.f * nu2 * m;
-        dpm = uj * uj * idx * m;
-        cp[0] = cpm;
-        dout[e] = dpm;
-      } else if (j < WG_NR - 1) {
-        const float r = j * DR, rinv = 1.f / r;
-        const float am = (1.f - HDR * rinv) * IDR2, ap = (1.f + HDR * rinv) * IDR2;
-        const float up = (up1 - um) * I2DR;
-        const float upr = up * rinv;
-        const float lap = fmaf(fmaf(-2.f, uj, up1 + um), IDR2, upr);
-        const float Ip = fmaf(HDR, rgp, I);
-        const float den = fmaf(-HDR, up, uj);
-        const float g = fmaf(upr, Ip, lap) * rcp_fast(den);
-        const float rg = r * g;
-        I = fmaf(HDR, rg, Ip);
-        rgp = rg;
-        const float Vd = -nu8 * rinv * I;        // nu * Vh_j / (2 dr)
-        const float a = fmaf(nu, am, Vd);        // -(sub-diagonal)
-        const float cc = fmaf(-nu, ap, Vd);      // super-diagonal
-        const float bb = fmaf(uj, idx, nu2);
-        float dd = uj * uj * idx;
-        if (j == WG_NR - 2) dd -= cc;            // Dirichlet U_63 = 1
-        const float m = rcp_fast(fmaf(a, cpm, bb));
-        cpm = cc * m;
-        dpm = fmaf(a, dpm, dd) * m;
-        cp[j] = cpm;
-        dout[e] = dpm;
-      } else {
-        dout[e] = 0.f;
-      }
-      um = uj;
+      const float2 nd = make_float2(j ? 1.f / (2.f * j) : 0.f, 0.5f * j);
+      WG_NODE_FWD(uu[e], uu[e + 1], um, nd, j == 0)
+      cp[j] = cpm;
+      dout[e] = dpm;
+      um = uu[e];
     }
-    if (c < WG_NR / 4 - 1) st_chunk(row, key, c, make_float4(dout[0], dout[1], dout[2], dout[3]));
-    else cur = make_float4(dout[0], dout[1], dout[2], 0.f);  // last chunk stays in registers: d'_60..62
-    if (c < WG_NR / 4 - 1) cur = nxt;
+    st_chunk(row, key, c, make_float4(dout[0], dout[1], dout[2], dout[3]));
+    cur = nxt;
   }
-  // ---- back substitution + shear integrals of the new profile
-  float un = 1.f, M = 0.f, umin = 1.f;
+  // ---- back substitution (U_63 = 1) + shear integrals of the new profile; slot 63 is rewritten afterwards
+  float un = 1.f, Mh = 0.f, umin = 1.f;
 #pragma unroll
   for (int c = WG_NR / 4 - 1; c >= 0; --c) {
-    float4 dq = (c == WG_NR / 4 - 1) ? cur : ld_chunk(row, key, c);
-    float dv[4] = {dq.x, dq.y, dq.z, dq.w};
+    const float4 dq = ld_chunk(row, key, c);
+    const float dv[4] = {dq.x, dq.y, dq.z, dq.w};
     float o[4];
 #pragma unroll
     for (int e = 3; e >= 0; --e) {
       const int j = 4 * c + e;
-      if (j == WG_NR - 1) { o[e] = 0.f; continue; }
-      un = (j == WG_NR - 2) ? dv[e] : fmaf(-cp[j], un, dv[e]);
+      if (j == WG_NR - 1) { o[e] = 0.f; continue; }  // node 63 carries no unknown
+      un = fmaf(-cp[j], un, dv[e]);
       o[e] = un;
-      M = fmaf(j * DR, 1.f - un, M);
+      Mh = fmaf(0.5f * j, 1.f - un, Mh);
       umin = fminf(umin, un);
     }
-    if (c < WG_NR / 4 - 1) st_chunk(row, key, c, make_float4(o[0], o[1], o[2], o[3]));
-    else cur = make_float4(o[0], o[1], o[2], 0.f);
+    st_chunk(row, key, c, make_float4(o[0], o[1], o[2], o[3]));
   }
-  cur.w = sqrtf(fmaxf(2.f * (M * DR) * (1.f - umin), 0.f));
-  st_chunk(row, key, WG_NR / 4 - 1, cur);
+  // M = dr^2 * sum j (1 - U_j) = 2 dr^2 Mh  ->  bw = sqrt(2 M (1 - Umin)) = 2 dr sqrt(Mh (1 - Umin))
+  row[(((WG_NR / 4 - 1) ^ key) << 2) | 3] = 2.f * DR * sqrtf(fmaxf(Mh * (1.f - umin), 0.f));
+  return un;
+}
+
+// Variant 1: both sweeps rolled (4 nodes per iteration), c' in a private shared-memory scratch row (same swizzle),
+// per-node grid constants from c_node.  Small code (instruction-cache resident), few registers, twice the shared
+// memory per station.
+__device__ __forceinline__ float march_row_smem(float* __restrict__ row, float* __restrict__ cps, int key, float dxt,
+                                                float xt, float knu1) {
+  constexpr float IDR2 = 1.f / (DR * DR);
+  float4 cur = ld_chunk(row, key, 0);
+  const float bw = ld_chunk(row, key, WG_NR / 4 - 1).w;
+  const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
+  const float idx = 1.f / fmaxf(dxt, DXT_MIN);
+  const float N = nu * IDR2, N2 = 2.f * N;
+  float I = 0.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < WG_NR / 4; ++c) {
+    float4 nxt = ld_chunk(row, key, min(c + 1, WG_NR / 4 - 1));
+    if (c + 1 == WG_NR / 4 - 1) nxt.w = 1.f;
+    const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+    float dout[4], cout[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 nd = c_node[4 * c + e];
+      WG_NODE_FWD(uu[e], uu[e + 1], um, nd, (e == 0 && c == 0))
+      cout[e] = cpm;
+      dout[e] = dpm;
+      um = uu[e];
+    }
+    st_chunk(row, key, c, make_float4(dout[0], dout[1], dout[2], dout[3]));
+    st_chunk(cps, key, c, make_float4(cout[0], cout[1], cout[2], cout[3]));
+    cur = nxt;
+  }
+  float un = 1.f, Mh = 0.f, umin = 1.f;
+#pragma unroll 1
+  for (int c = WG_NR / 4 - 1; c >= 0; --c) {
+    const float4 dq = ld_chunk(row, key, c);
+    const float4 cq = ld_chunk(cps, key, c);
+    const float dv[4] = {dq.x, dq.y, dq.z, dq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+    float o[4];
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+      const float2 nd = c_node[4 * c + e];
+      const float cand = fmaf(-cv[e], un, dv[e]);
+      if (e == 3 && c == WG_NR / 4 - 1) {
+        o[e] = 0.f;  // node 63 carries no unknown (its d', c' are dummies)
+      } else {
+        un = cand;
+        o[e] = un;
+        Mh = fmaf(nd.y, 1.f - un, Mh);
+        umin = fminf(umin, un);
+      }
+    }
+    st_chunk(row, key, c, make_float4(o[0], o[1], o[2], o[3]));
+  }
+  row[(((WG_NR / 4 - 1) ^ key) << 2) | 3] = 2.f * DR * sqrtf(fmaxf(Mh * (1.f - umin), 0.f));
   return un;
 }
 
@@ -285,10 +348,11 @@ __device__ __forceinline__ Seg segments(const LaneLoc& L, int lane) {
 }
 
 // Evaluate the queued (station row, rotor) hits of one warp: two hits per pass, 16 quadrature points each on
-// 16 lanes, shuffle-reduced to the rotor average, accumulated per (rotor, emitting chain).
-__device__ __forceinline__ void flush_hits(const float* __restrict__ tile, const float4* __restrict__ ha,
-                                           const int2* __restrict__ hb, int nh, float* acc_du, float* acc_dv,
-                                           int lane, float qy, float qz) {
+// 16 lanes, shuffle-reduced to the rotor average, accumulated per rotor in the warp's private accumulators
+// (fixed order -> bit-reproducible; the turbine epilogue adds the warps' partial sums).
+__device__ __noinline__ void flush_hits(const float* __restrict__ tile, const float4* __restrict__ ha,
+                                        const int2* __restrict__ hb, int nh, float* acc_du, float* acc_dv,
+                                        int lane, float qy, float qz) {
   const unsigned full = 0xffffffffu;
   const int half = lane >> 4;
   for (int h0 = 0; h0 < nh; h0 += 2) {
@@ -312,23 +376,26 @@ __device__ __forceinline__ void flush_hits(const float* __restrict__ tile, const
     d += __shfl_xor_sync(full, d, 4);
     d += __shfl_xor_sync(full, d, 2);
     d += __shfl_xor_sync(full, d, 1);
-    if ((lane & 15) == 0 && ok) {
-      d *= (1.f / WG_NQ);
-      atomicAdd(&acc_du[b.y], a.x * d);
-      atomicAdd(&acc_dv[b.y], a.y * d);
+    d *= (1.f / WG_NQ);
+    if (lane == 0) {
+      acc_du[b.y] = fmaf(a.x, d, acc_du[b.y]);
+      acc_dv[b.y] = fmaf(a.y, d, acc_dv[b.y]);
     }
+    __syncwarp();
+    if (lane == 16 && ok) {
+      acc_du[b.y] = fmaf(a.x, d, acc_du[b.y]);
+      acc_dv[b.y] = fmaf(a.y, d, acc_dv[b.y]);
+    }
+    __syncwarp();
   }
 }
 
-template <int NSTAGE>
-__global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
+template <int VARIANT>
+__global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FlowShared& sh = *reinterpret_cast<FlowShared*>(smem_raw);
   const int T = d.T, P = d.P, F = d.F;
-  float* acc_du = reinterpret_cast<float*>(smem_raw + ((sizeof(FlowShared) + 127) / 128) * 128);
-  float* acc_dv = acc_du + T * T;
-  float* bufs = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(acc_du) +
-                                         (((size_t)2 * T * T * sizeof(float) + 127) / 128) * 128);
+  float* bufs = reinterpret_cast<float*>(smem_raw + ((sizeof(FlowShared) + 127) / 128) * 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / F, f = blockIdx.x % F;
@@ -347,8 +414,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
   float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;
   float* pmut0 = d.pmut + (size_t)bf * T * P * 4;
   float* pmut1 = pmut0 + (size_t)d.B * F * T * P * 4;
-  float* my_buf = bufs + (size_t)warp * NSTAGE * WG_TILE * WG_NR;
+  float* tile_base = bufs + (size_t)warp * (VARIANT == 0 ? 1 : 2) * WG_TILE * WG_NR;
+  float* row = tile_base + lane * WG_NR;
+  float* cps = row + WG_TILE * WG_NR;  // variant 1: c' scratch row behind the warp's tile
+  (void)cps;
   const float qy = c_qy[lane & 15], qz = c_qz[lane & 15];
+  void* bar = &sh.mbar[warp];
 
   if (tid < T) {
     sh.xr[tid] = d.xr[b * T + tid];
@@ -377,8 +448,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
   }
   if (tid == 0) sh.base_sum = 0.f;
   if (lane == 0) {
-    mbar_init(&sh.mbar[warp][0], 1);
-    mbar_init(&sh.mbar[warp][1], 1);
+    mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   int nstep = d.n_step[bf];
@@ -395,6 +465,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
     sh.ord[rank] = tid;
   }
   __syncthreads();
+  // sorted rotor-plane positions held across the lanes of every warp (T <= 64): range queries by ballot
+  const float xs_a = lane < T ? sh.xs[lane] : CUDART_INF_F;
+  const float xs_b = lane + 32 < T ? sh.xs[lane + 32] : CUDART_INF_F;
+  const float x_retire = xmax + MARGIN_D * d.D;
 
   for (int sub = 0; sub < nsteps; ++sub) {
     const float* __restrict__ pm_old = (nstep & 1) ? pmut1 : pmut0;
@@ -424,11 +498,14 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
         float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)tid * P + s) * 4));
         float xn, yn, zn, dx;
         moved(pm, pc, ws, dt, xn, yn, zn, dx);
-        if (xn > xmax + MARGIN_D * d.D) --cnt; else break;
+        if (xn > x_retire) --cnt; else break;
       }
       sh.count[tid] = cnt;
     }
-    for (int i = tid; i < 2 * T * T; i += blockDim.x) acc_du[i] = 0.f;
+    for (int i = tid; i < WG_NWARP * WG_MAX_T; i += blockDim.x) {
+      (&sh.acc_du[0][0])[i] = 0.f;
+      (&sh.acc_dv[0][0])[i] = 0.f;
+    }
     __syncthreads();
     if (tid == 0) {
       int s = 0;
@@ -440,72 +517,60 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
     const int ntiles = (ntot + WG_TILE - 1) / WG_TILE;
 
     // ------------------------------------------------------------------ warp-private tile pipeline
-    LaneLoc Lc, Ln;
-    float4 pmc, pcc, pmn, pcn;
-    int stage = 0;
-    Lc.valid = 0; Lc.chain = 0; Lc.slot = 0; Lc.q = 0;
-    pmc = pcc = pmn = pcn = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto issue_load = [&](const LaneLoc& L, int stg) {
-      Seg sg = segments(L, lane);
-      void* bar = &sh.mbar[warp][stg];
+    float* acc_du = sh.acc_du[warp];
+    float* acc_dv = sh.acc_dv[warp];
+    float4* ha = sh.hit_a[warp];
+    int2* hb = sh.hit_b[warp];
+    const unsigned full = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    int tile = warp;
+    LaneLoc Ln;
+    Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
+    if (tile < ntiles) Ln = locate(sh, tile, lane, T, P, ntot);
+    while (tile < ntiles) {
+      const LaneLoc Lc = Ln;
+      const Seg sg = segments(Lc, lane);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)sg.nvalid * WG_ROW_BYTES);
       __syncwarp();
-      if (sg.start)
-        bulk_g2s(my_buf + ((size_t)stg * WG_TILE + lane) * WG_NR, prof + ((size_t)L.chain * P + L.slot) * WG_NR,
-                 (uint32_t)sg.len * WG_ROW_BYTES, bar);
-    };
-    auto load_scalars = [&](const LaneLoc& L, float4& pm, float4& pc) {
-      if (L.valid) {
-        pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)L.chain * P + L.slot) * 4));
-        pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)L.chain * P + L.slot) * 4));
+      float* gsrc = prof + ((size_t)Lc.chain * P + Lc.slot) * WG_NR;
+      if (sg.start) bulk_g2s(row, gsrc, (uint32_t)sg.len * WG_ROW_BYTES, bar);
+      float4 pmc = make_float4(0.f, 0.f, 0.f, 0.f), pcc = pmc;
+      if (Lc.valid) {
+        pmc = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + Lc.slot) * 4));
+        pcc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + Lc.slot) * 4));
       }
-    };
-    if (warp < ntiles) {
-      Lc = locate(sh, warp, lane, T, P, ntot);
-      issue_load(Lc, 0);
-      load_scalars(Lc, pmc, pcc);
-    }
-    for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
+      // while the tile is in flight: find the next one and pull its rows towards L2
       const int nt = tile + WG_NWARP;
-      Ln.valid = 0;
-      if (nt < ntiles) Ln = locate(sh, nt, lane, T, P, ntot);
-      if (NSTAGE == 2) {
-        bulk_wait_read0();  // stores that used the other stage have drained their shared-memory reads
-        __syncwarp();
-        if (nt < ntiles) issue_load(Ln, stage ^ 1);
+      if (nt < ntiles) {
+        Ln = locate(sh, nt, lane, T, P, ntot);
+        if (Ln.valid)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + ((size_t)Ln.chain * P + Ln.slot) * WG_NR));
       }
-      if (nt < ntiles) load_scalars(Ln, pmn, pcn);
-      mbar_wait(&sh.mbar[warp][stage], (phase >> stage) & 1u);
-      phase ^= (1u << stage);
-
-      float* tile_base = my_buf + (size_t)stage * WG_TILE * WG_NR;
-      float* row = tile_base + lane * WG_NR;
       const int key = Lc.slot & 7;
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
+      if (Lc.valid) moved(pmc, pcc, ws, dt, xn, yn, zn, dx);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
       if (Lc.valid) {
-        moved(pmc, pcc, ws, dt, xn, yn, zn, dx);
-        float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
-        float ucn = march_row(row, key, dx * rR, xt_mid, pcc.y);
+        const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
+        const float ucn = VARIANT == 0 ? march_row_regs(row, key, dx * rR, xt_mid, pcc.y)
+                                       : march_row_smem(row, cps, key, dx * rR, xt_mid, pcc.y);
         *reinterpret_cast<float4*>(pm_new + ((size_t)Lc.chain * P + Lc.slot) * 4) = make_float4(xn, yn, zn, ucn);
       }
       fence_async_smem();
       __syncwarp();
-      {  // write the marched rows back (same segments as the load)
-        Seg sg = segments(Lc, lane);
-        if (sg.start) {
-          bulk_s2g(prof + ((size_t)Lc.chain * P + Lc.slot) * WG_NR, row, (uint32_t)sg.len * WG_ROW_BYTES);
-          bulk_commit();
-        }
+      if (sg.start) {  // write the marched rows back (same segments as the load)
+        bulk_s2g(gsrc, row, (uint32_t)sg.len * WG_ROW_BYTES);
+        bulk_commit();
       }
       // ---- superposition: which rotor planes does this station bracket together with its age neighbours?
       {
-        const unsigned full = 0xffffffffu;
         // older neighbour = flat index - 1 (same chain), younger = flat index + 1
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
-        int co = __shfl_up_sync(full, Lc.chain, 1);
+        const int co = __shfl_up_sync(full, Lc.chain, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        int cy = __shfl_down_sync(full, Lc.chain, 1);
-        int vy_ = __shfl_down_sync(full, Lc.valid, 1);
+        const int cy = __shfl_down_sync(full, Lc.chain, 1);
+        const int vy_ = __shfl_down_sync(full, Lc.valid, 1);
         const bool has_o = Lc.valid && Lc.q > 0;
         const bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
         if (has_o && (lane == 0 || co != Lc.chain)) {
@@ -522,72 +587,64 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
           float dxx;
           moved(pm, pc, ws, dt, xy, yy, zy, dxx);
         }
+        if (!has_o) { xo = xn; yo = yn; zo = zn; }  // degenerate intervals never bracket anything
+        if (!has_y) { xy = xn; yy = yn; zy = zn; }
         // x-range touched by this tile (warp-uniform): only rotor planes inside it can be bracketed
-        float lo = Lc.valid ? xn : CUDART_INF_F, hi = Lc.valid ? xn : -CUDART_INF_F;
-        if (has_o) { lo = fminf(lo, xo); hi = fmaxf(hi, xo); }
-        if (has_y) { lo = fminf(lo, xy); hi = fmaxf(hi, xy); }
+        float lo = Lc.valid ? fminf(xn, fminf(xo, xy)) : CUDART_INF_F;
+        float hi = Lc.valid ? fmaxf(xn, fmaxf(xo, xy)) : -CUDART_INF_F;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           lo = fminf(lo, __shfl_xor_sync(full, lo, o));
           hi = fmaxf(hi, __shfl_xor_sync(full, hi, o));
         }
+        // sorted rotor planes with lo <= x < hi: [k0, k1)
+        const int k0 = __popc(__ballot_sync(full, xs_a < lo)) + __popc(__ballot_sync(full, xs_b < lo));
+        const int k1 = __popc(__ballot_sync(full, xs_a < hi)) + __popc(__ballot_sync(full, xs_b < hi));
         const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
-        float4* ha = sh.hit_a[warp];
-        int2* hb = sh.hit_b[warp];
-        const unsigned lt = (1u << lane) - 1u;
         const int rowkey = lane | (key << 8);
         int nh = 0;
-        int k = 0;
-        while (k < T && sh.xs[k] < lo) ++k;
-        for (; k < T; ++k) {
+        for (int k = k0; k < k1; ++k) {
           const float xj = sh.xs[k];
-          if (xj >= hi) break;
           const int j = sh.ord[k];
+          // interval A: [self (younger end), older neighbour); interval B: [younger neighbour, self (older end)).
+          // sign +1 for the regular downstream-ordered pair, -1 if the pair is inverted (oracle/dwm_numpy.py:353-356)
+          const bool pn = xn <= xj, po = xo <= xj, py = xy <= xj;
           const bool mine = Lc.valid && j != Lc.chain;
-          // interval A: (self = younger end, older neighbour); interval B: (younger neighbour, self = older end)
-          float sgA = 0.f, sgB = 0.f;
-          if (mine && has_o) sgA = (xn <= xj && xj < xo) ? 1.f : ((xo <= xj && xj < xn) ? -1.f : 0.f);
-          if (mine && has_y) sgB = (xy <= xj && xj < xn) ? 1.f : ((xn <= xj && xj < xy) ? -1.f : 0.f);
-          const unsigned mA = __ballot_sync(full, sgA != 0.f), mB = __ballot_sync(full, sgB != 0.f);
+          const bool hitA = mine && (pn != po), hitB = mine && (py != pn);
+          const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
           if ((mA | mB) == 0u) continue;
           const float yrj = sh.yr[j];
-          if (sgA != 0.f) {
-            const float w = (xj - xn) / (xo - xn);
-            const float wg = sgA * (1.f - w);
-            const float yc = yn * (1.f - w) + yo * w, zc = zn * (1.f - w) + zo * w;
+          if (hitA) {
+            const float w = (xj - xn) * rcp_fast(xo - xn);
+            const float wg = pn ? 1.f - w : w - 1.f;
+            const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
             const int p = nh + __popc(mA & lt);
             ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
-            hb[p] = make_int2(rowkey, j * T + Lc.chain);
+            hb[p] = make_int2(rowkey, j);
           }
           nh += __popc(mA);
-          if (sgB != 0.f) {
-            const float w = (xj - xy) / (xn - xy);
-            const float wg = sgB * w;
-            const float yc = yy * (1.f - w) + yn * w, zc = zy * (1.f - w) + zn * w;
+          if (hitB) {
+            const float w = (xj - xy) * rcp_fast(xn - xy);
+            const float wg = py ? w : -w;
+            const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
             const int p = nh + __popc(mB & lt);
             ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
-            hb[p] = make_int2(rowkey, j * T + Lc.chain);
+            hb[p] = make_int2(rowkey, j);
           }
           nh += __popc(mB);
           if (nh > WG_HIT_CAP - 64) {
             __syncwarp();
             flush_hits(tile_base, ha, hb, nh, acc_du, acc_dv, lane, qy, qz);
-            __syncwarp();
             nh = 0;
           }
         }
         __syncwarp();
-        flush_hits(tile_base, ha, hb, nh, acc_du, acc_dv, lane, qy, qz);
+        if (nh > 0) flush_hits(tile_base, ha, hb, nh, acc_du, acc_dv, lane, qy, qz);
       }
       __syncwarp();
-      if (NSTAGE == 1) {
-        bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
-        __syncwarp();
-        if (nt < ntiles) issue_load(Ln, 0);
-      } else {
-        stage ^= 1;
-      }
-      Lc = Ln; pmc = pmn; pcc = pcn;
+      bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
+      __syncwarp();
+      tile = nt;
     }
     bulk_wait_all0();
     fence_async_all();
@@ -597,7 +654,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
     const bool emit = (nstep % k_emit) == 0;
     if (tid < T) {
       float du = 0.f, dv = 0.f;
-      for (int i = 0; i < T; ++i) { du += acc_du[tid * T + i]; dv += acc_dv[tid * T + i]; }
+#pragma unroll
+      for (int wi = 0; wi < WG_NWARP; ++wi) { du += sh.acc_du[wi][tid]; dv += sh.acc_dv[wi][tid]; }
       const float u = ws - du, v = dv, w = 0.f;
       const float yaw = sh.yaw[tid];
       float sg, cg;
@@ -607,29 +665,13 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
       float ct = tab_interp(d.tab_ws, d.tab_ct, d.n_tab, wse) * cg * cg;
       ct = fminf(fmaxf(ct, 0.f), CT_MAX);
       sh.u[tid] = u; sh.v[tid] = v; sh.w[tid] = w; sh.pw[tid] = pw; sh.ct[tid] = ct;
+      sh.cg[tid] = cg; sh.sg[tid] = sg;
       int slot = -1;
       if (emit) {
-        const float ind = 0.5f * (1.f - sqrtf(1.f - ct));
-        sh.ind[tid] = ind;
+        sh.ind[tid] = 0.5f * (1.f - sqrtf(1.f - ct));
         slot = sh.head[tid];
         if (sh.count[tid] == P) atomicOr(&d.flags[b], 2); else sh.count[tid] += 1;
         sh.head[tid] = (slot + 1 == P) ? 0 : slot + 1;
-        // cell-averaged top-hat inlet (same formula as the row writer below): centre value and shear integral
-        const float fw = 1.f - 0.45f * ind * ind;
-        const float rw2 = fw * fw * (1.f - ind) / (1.f - 2.f * ind);
-        float M = 0.f, u0v = 1.f;
-        for (int j = 0; j < WG_NR - 1; ++j) {
-          const float rlo = fmaxf((float)j - 0.5f, 0.f) * DR, rhi = ((float)j + 0.5f) * DR;
-          const float frac = fminf(fmaxf((rw2 - rlo * rlo) / (rhi * rhi - rlo * rlo), 0.f), 1.f);
-          const float df = 2.f * ind * frac;
-          if (j == 0) u0v = 1.f - df;
-          M = fmaf((float)j * DR, df, M);
-        }
-        // the inlet is monotone non-decreasing in r, so Umin is the centre value
-        sh.bw0[tid] = sqrtf(fmaxf(2.f * (M * DR) * (1.f - u0v), 0.f));
-        *reinterpret_cast<float4*>(pm_new + ((size_t)tid * P + slot) * 4) =
-            make_float4(sh.xr[tid], sh.yr[tid], d.zh, u0v);
-        *reinterpret_cast<float4*>(pcon + ((size_t)tid * P + slot) * 4) = make_float4(u, knu1_env, cg, sg);
       }
       sh.emit_slot[tid] = slot;
       if (a.mode == FLOW_STEP) {
@@ -647,24 +689,40 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
       for (int t = 0; t < T; ++t) s += sh.pw[t];
       sh.base_sum += s;
     }
-    if (emit) {  // release one particle per turbine: cell-averaged top-hat inlet (IEC 61400-1 ed.4 Annex E)
-      for (int idx = tid; idx < T * (WG_NR / 4); idx += blockDim.x) {
+    if (emit) {
+      // release one particle per turbine: cell-averaged top-hat inlet (IEC 61400-1 ed.4 Annex E).  16 threads per
+      // turbine write one 16-byte chunk each and shuffle-reduce the row's shear integral into slot 63.
+      for (int idx = tid; idx < T * (WG_NR / 4); idx += blockDim.x) {  // T*16 is a multiple of 16: half-warps stay whole
         const int t = idx >> 4, c = idx & 15;
         const int slot = sh.emit_slot[t];
-        if (slot < 0) continue;
         const float ind = sh.ind[t];
         const float fw = 1.f - 0.45f * ind * ind;
         const float rw2 = fw * fw * (1.f - ind) / (1.f - 2.f * ind);
-        float vals[4];
+        float vals[4], Mh = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int j = 4 * c + e;
           const float rlo = fmaxf((float)j - 0.5f, 0.f) * DR, rhi = ((float)j + 0.5f) * DR;
           const float frac = fminf(fmaxf((rw2 - rlo * rlo) / (rhi * rhi - rlo * rlo), 0.f), 1.f);
-          vals[e] = (j == WG_NR - 1) ? sh.bw0[t] : 1.f - 2.f * ind * frac;
+          const float df = (j == WG_NR - 1) ? 0.f : 2.f * ind * frac;
+          vals[e] = 1.f - df;
+          Mh = fmaf(0.5f * (float)j, df, Mh);
         }
+        const unsigned hm = 0xffffu << (lane & 16);
+        Mh += __shfl_xor_sync(hm, Mh, 8);
+        Mh += __shfl_xor_sync(hm, Mh, 4);
+        Mh += __shfl_xor_sync(hm, Mh, 2);
+        Mh += __shfl_xor_sync(hm, Mh, 1);
+        const float u0v = __shfl_sync(hm, vals[0], lane & 16);  // centre value = Umin of the monotone inlet
+        if (slot < 0) continue;
+        if (c == WG_NR / 4 - 1) vals[3] = 2.f * DR * sqrtf(fmaxf(Mh * (1.f - u0v), 0.f));
         *reinterpret_cast<float4*>(prof + ((size_t)t * P + slot) * WG_NR + ((c ^ (slot & 7)) << 2)) =
             make_float4(vals[0], vals[1], vals[2], vals[3]);
+        if (c == 0) {
+          *reinterpret_cast<float4*>(pm_new + ((size_t)t * P + slot) * 4) = make_float4(sh.xr[t], sh.yr[t], d.zh, u0v);
+          *reinterpret_cast<float4*>(pcon + ((size_t)t * P + slot) * 4) =
+              make_float4(sh.u[t], knu1_env, sh.cg[t], sh.sg[t]);
+        }
       }
       fence_async_all();
     }
@@ -695,30 +753,30 @@ __global__ void __launch_bounds__(WG_NWARP * 32, NSTAGE == 1 ? 4 : 3) wg_flow_ke
   }
 }
 
-// Tile buffers per warp: 1 (default; 4 CTAs/SM, latency hidden by the other warps) or 2 (WG_FLOW_STAGES=2; the next
-// tile is prefetched while the current one is marched, 3 CTAs/SM).
-static int flow_stages() {
-  static int n = 0;
-  if (n == 0) {
-    const char* e = getenv("WG_FLOW_STAGES");
-    n = (e && e[0] == '2') ? 2 : 1;
+// Variant 0 (default): c' in registers, unrolled march, 4 CTAs/SM.  Variant 1 (WG_FLOW_VARIANT=1): c' in shared
+// memory, rolled march, 3 CTAs/SM.
+static int flow_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("WG_FLOW_VARIANT");
+    v = (e && e[0] == '1') ? 1 : 0;
   }
-  return n;
+  return v;
 }
 
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  const int ns = flow_stages();
-  const size_t smem = flow_smem_bytes(d.T, ns);
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > configured[ns]) {
-    cudaError_t e = ns == 1
-        ? cudaFuncSetAttribute(wg_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-        : cudaFuncSetAttribute(wg_flow_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int v = flow_variant();
+  const size_t smem = flow_smem_bytes(d.T, v == 0 ? 1 : 2);
+  static bool configured[2] = {false, false};
+  if (!configured[v]) {
+    cudaError_t e = v == 0
+        ? cudaFuncSetAttribute(wg_flow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(wg_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[ns] = smem;
+    configured[v] = true;
   }
-  if (ns == 1) wg_flow_kernel<1><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
-  else wg_flow_kernel<2><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  if (v == 0) wg_flow_kernel<0><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  else wg_flow_kernel<1><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
 
