@@ -390,7 +390,7 @@ __device__ __noinline__ void flush_hits(const float* __restrict__ tile, const fl
   }
 }
 
-template <int VARIANT>
+template <int VARIANT, int SYNC_ROUNDS>
 __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FlowShared& sh = *reinterpret_cast<FlowShared*>(smem_raw);
@@ -527,7 +527,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
     LaneLoc Ln;
     Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
     if (tile < ntiles) Ln = locate(sh, tile, lane, T, P, ntot);
-    while (tile < ntiles) {
+    const int nrounds = (ntiles + WG_NWARP - 1) / WG_NWARP;
+    for (int rnd = 0; rnd < nrounds; ++rnd) {
+      if (SYNC_ROUNDS) __syncthreads();  // the CTA's warps (one per SM sub-partition) enter the march together
+      if (tile >= ntiles) continue;
       const LaneLoc Lc = Ln;
       const Seg sg = segments(Lc, lane);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)sg.nvalid * WG_ROW_BYTES);
@@ -754,29 +757,28 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
 }
 
 // Variant 0 (default): c' in registers, unrolled march, 4 CTAs/SM.  Variant 1 (WG_FLOW_VARIANT=1): c' in shared
-// memory, rolled march, 3 CTAs/SM.
-static int flow_variant() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("WG_FLOW_VARIANT");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
+// memory, rolled march.  WG_FLOW_SYNC=1: the CTA's warps start every tile round together (instruction-cache sharing).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
 }
 
+typedef void (*flow_fn)(const Dev, const FlowArgs);
+
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  const int v = flow_variant();
+  static const int v = env_int("WG_FLOW_VARIANT", 0) ? 1 : 0;
+  static const int sync = env_int("WG_FLOW_SYNC", 1) ? 1 : 0;
+  static const flow_fn fns[2][2] = {{wg_flow_kernel<0, 0>, wg_flow_kernel<0, 1>},
+                                    {wg_flow_kernel<1, 0>, wg_flow_kernel<1, 1>}};
+  const flow_fn fn = fns[v][sync];
   const size_t smem = flow_smem_bytes(d.T, v == 0 ? 1 : 2);
-  static bool configured[2] = {false, false};
-  if (!configured[v]) {
-    cudaError_t e = v == 0
-        ? cudaFuncSetAttribute(wg_flow_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-        : cudaFuncSetAttribute(wg_flow_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured[v] = true;
+    configured = true;
   }
-  if (v == 0) wg_flow_kernel<0><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
-  else wg_flow_kernel<1><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  fn<<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
 
