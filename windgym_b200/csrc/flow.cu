@@ -31,8 +31,7 @@ __constant__ float c_qy[WG_NQ];
 __constant__ float c_qz[WG_NQ];
 
 
-#define WG_NWARP 4        // warps per CTA
-#define WG_HIT_CAP 96     // per-warp hit list entries (flushed when fewer than 64 free)
+#define WG_HIT_CAP 64     // per-warp hit list entries (one detection pass adds at most 2 x 32)
 
 // per-node constants of the radial grid r_j = j dr: {1/(2j), j/2}; entry 0 unused (the axis node has its own row)
 __constant__ float2 c_node[WG_NR];
@@ -46,27 +45,26 @@ void set_rotor_points(const float* qy, const float* qz) {
   cudaMemcpyToSymbol(c_node, nd, sizeof(nd));
 }
 
+// Per-CTA bookkeeping in front of the tile buffers.  NW = warps per CTA, TC = turbine capacity of the tables
+// (16 or WG_MAX_T: small farms leave the shared memory to more resident CTAs).
+template <int NW, int TC>
 struct __align__(16) FlowShared {
-  unsigned long long mbar[WG_NWARP];
-  float xr[WG_MAX_T], yr[WG_MAX_T], yaw[WG_MAX_T], u[WG_MAX_T], v[WG_MAX_T], w[WG_MAX_T], pw[WG_MAX_T],
-      ct[WG_MAX_T], ind[WG_MAX_T], cg[WG_MAX_T], sg[WG_MAX_T];
-  float xs[WG_MAX_T];                       // turbine x sorted ascending
-  float sum_ws[WG_MAX_T], sum_wd[WG_MAX_T], sum_yaw[WG_MAX_T], sum_pw[WG_MAX_T];
-  float acc_du[WG_NWARP][WG_MAX_T], acc_dv[WG_NWARP][WG_MAX_T];  // per-warp superposed deficit per rotor
-  int ord[WG_MAX_T];                        // turbine index of xs[k]
-  int head[WG_MAX_T], count[WG_MAX_T], pre[WG_MAX_T + 1], emit_slot[WG_MAX_T];
+  unsigned long long mbar[NW];
+  float xr[TC], yr[TC], yaw[TC], u[TC], v[TC], w[TC], pw[TC], ct[TC], ind[TC], cg[TC], sg[TC];
+  float xs[2 * TC];                         // turbine x sorted ascending, padded with +inf
+  float sum_ws[TC], sum_wd[TC], sum_yaw[TC], sum_pw[TC];
+  float acc_du[NW][TC], acc_dv[NW][TC];     // per-warp superposed deficit per rotor
+  int ord[TC];                              // turbine index of xs[k]
+  int head[TC], count[TC], pre[TC + 1], emit_slot[TC];
   float base_sum;
-  int pad[3];
-  float4 hit_a[WG_NWARP][WG_HIT_CAP];       // w*U0e*cos g0, w*U0e*sin g0, ry, rz
-  int2 hit_b[WG_NWARP][WG_HIT_CAP];         // (row | key << 8), rotor index j
+  uint32_t tmem_base;                       // variant 2: TMEM allocation of the CTA
+  int pad[1];
+  float4 hit_a[NW][WG_HIT_CAP];             // w*U0e*cos g0, w*U0e*sin g0, ry, rz
+  int2 hit_b[NW][WG_HIT_CAP];               // (row | key << 8), rotor index j
 };
 
-static size_t hdr_bytes() { return (sizeof(FlowShared) + 127) / 128 * 128; }
-
-size_t flow_smem_bytes(int T, int n_stage) {
-  (void)T;
-  return hdr_bytes() + (size_t)WG_NWARP * n_stage * WG_TILE * WG_ROW_BYTES;
-}
+template <int NW, int TC>
+__host__ __device__ constexpr size_t hdr_bytes() { return (sizeof(FlowShared<NW, TC>) + 127) / 128 * 128; }
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -174,6 +172,7 @@ __device__ __forceinline__ void st_chunk(float* row, int key, int c, float4 v) {
 // statically indexed.  With h = 1/(2j), N = nu/dr^2:
 //   lap_j dr^2 = U_{j+1} + U_{j-1} - 2 U_j + h (U_{j+1} - U_{j-1}),  Vd_j = nu Vh_j / (2 dr) = -N h I_j,
 //   sub-diagonal -a_j = -(N - N h (1 + I_j)), super-diagonal c_j = -N - N h (1 + I_j), diagonal U_j/dx + 2N.
+// The sweep carries W = 1 + I: lap_j dr^2 + h dU (I + rgh) = (su - 2 U_j) + h dU (W + rgh).
 // Node j of the forward sweep (shared by both march variants).  nd = {1/(2j), j/2}.
 #define WG_NODE_FWD(uj, up1, um, nd, AXIS)                                              \
   {                                                                                     \
@@ -184,16 +183,15 @@ __device__ __forceinline__ void st_chunk(float* row, int key, int c, float4 v) {
     } else {                                                                            \
       const float du = (up1) - (um), su = (up1) + (um);                                 \
       const float hd = (nd).x * du;                                                     \
-      const float t2 = fmaf(-2.f, (uj), hd + su);                                       \
-      const float Ip = I + rgh;                                                         \
+      const float t2 = fmaf(-2.f, (uj), su);      /* lap dr^2 - hd */                   \
+      const float Wp = W + rgh;                   /* W = 1 + I */                       \
       const float den = fmaf(-0.25f, du, (uj));                                         \
-      const float G = fmaf(hd, Ip, t2) * rcp_fast(den);                                 \
+      const float G = fmaf(hd, Wp, t2) * rcp_fast(den);                                 \
       rgh = (nd).y * G;                                                                 \
-      I = Ip + rgh;                                                                     \
-      const float nh = N * (nd).x;                                                      \
-      const float t = fmaf(-nh, I, -nh);                                                \
-      a = t + N;                                                                        \
-      cc = t - N;                                                                       \
+      W = Wp + rgh;                                                                     \
+      const float q = (nd).x * W;                 /* h (1 + I) */                       \
+      a = fmaf(-N, q, N);                                                               \
+      cc = fmaf(-N, q, -N);                                                             \
     }                                                                                   \
     const float m = rcp_fast(fmaf(a, cpm, bb));                                         \
     cpm = cc * m;                                                                       \
@@ -209,7 +207,7 @@ __device__ __forceinline__ float march_row_regs(float* __restrict__ row, int key
   const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
   const float idx = 1.f / fmaxf(dxt, DXT_MIN);
   const float N = nu * IDR2, N2 = 2.f * N;
-  float I = 0.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
+  float W = 1.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
 #pragma unroll
   for (int c = 0; c < WG_NR / 4; ++c) {
     float4 nxt = cur;
@@ -263,7 +261,7 @@ __device__ __forceinline__ float march_row_smem(float* __restrict__ row, float* 
   const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
   const float idx = 1.f / fmaxf(dxt, DXT_MIN);
   const float N = nu * IDR2, N2 = 2.f * N;
-  float I = 0.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
+  float W = 1.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
 #pragma unroll 1
   for (int c = 0; c < WG_NR / 4; ++c) {
     float4 nxt = ld_chunk(row, key, min(c + 1, WG_NR / 4 - 1));
@@ -308,11 +306,142 @@ __device__ __forceinline__ float march_row_smem(float* __restrict__ row, float* 
   return un;
 }
 
+// ---------------------------------------------------------------------------------------------- TMEM scratch
+// Variant 2 keeps the Thomas coefficients c' in Blackwell tensor memory instead of 63 registers: every thread owns
+// one TMEM lane (warp w of the CTA addresses lanes 32 (w & 3) .. +31), node j lives in column j of the CTA's
+// 64-column allocation.  tcgen05.st / tcgen05.ld with shape 32x32b move 4 consecutive columns of the thread's own
+// lane per instruction (SASS STTM / LDTM), so TMEM acts as a software-managed per-thread scratch; nothing here
+// touches the tensor cores.  The freed registers buy a fifth resident CTA per SM and let the march be a rolled
+// loop that stays inside the instruction cache.
+#define WG_TMEM_COLS 64
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+               "n"(WG_TMEM_COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(WG_TMEM_COLS) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, float a, float b, float c, float d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ float4 tmem_ld4(uint32_t taddr) {
+  float4 v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(taddr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Variant 2: both sweeps rolled over the row's sixteen 4-node chunks, c' in the thread's TMEM lane (taddr = lane
+// base + column 0).  Executed by all 32 lanes of the warp (tcgen05.ld/st are warp-collective).
+__device__ __forceinline__ float march_row_tmem(float* __restrict__ row, uint32_t taddr, int key, float dxt, float xt,
+                                                float knu1) {
+  constexpr float IDR2 = 1.f / (DR * DR);
+  constexpr int NC = WG_NR / 4;
+  float4 cur = ld_chunk(row, key, 0);
+  const float bw = ld_chunk(row, key, NC - 1).w;
+  const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
+  const float idx = 1.f / fmaxf(dxt, DXT_MIN);
+  const float N = nu * IDR2, N2 = 2.f * N;
+  float W = 1.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
+  {  // chunk 0 holds the axis node
+    const float4 nxt = ld_chunk(row, key, 1);
+    const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+    float dout[4], cout[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 nd = make_float2(e ? 1.f / (2.f * e) : 0.f, 0.5f * e);
+      WG_NODE_FWD(uu[e], uu[e + 1], um, nd, e == 0)
+      cout[e] = cpm;
+      dout[e] = dpm;
+      um = uu[e];
+    }
+    st_chunk(row, key, 0, make_float4(dout[0], dout[1], dout[2], dout[3]));
+    tmem_st4(taddr, cout[0], cout[1], cout[2], cout[3]);
+    cur = nxt;
+  }
+#pragma unroll 1
+  for (int c = 1; c < NC; ++c) {
+    float4 nxt = ld_chunk(row, key, min(c + 1, NC - 1));
+    if (c + 1 == NC - 1) nxt.w = 1.f;  // Dirichlet node: the slot holds bw, the value is 1
+    const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
+    float dout[4], cout[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 nd = c_node[4 * c + e];
+      WG_NODE_FWD(uu[e], uu[e + 1], um, nd, false)
+      cout[e] = cpm;
+      dout[e] = dpm;
+      um = uu[e];
+    }
+    st_chunk(row, key, c, make_float4(dout[0], dout[1], dout[2], dout[3]));
+    tmem_st4(taddr + 4 * c, cout[0], cout[1], cout[2], cout[3]);
+    cur = nxt;
+  }
+  tmem_wait_st();
+  // ---- back substitution (U_63 = 1); chunk 15 carries the Dirichlet slot and is peeled
+  float un = 1.f, Mh = 0.f, umin = 1.f;
+  float4 cq = tmem_ld4(taddr + 4 * (NC - 1));
+  tmem_wait_ld();
+  {
+    const float4 dq = ld_chunk(row, key, NC - 1);
+    float4 cn = tmem_ld4(taddr + 4 * (NC - 2));
+    float o[3];
+    const float dv[3] = {dq.x, dq.y, dq.z}, cv[3] = {cq.x, cq.y, cq.z};
+#pragma unroll
+    for (int e = 2; e >= 0; --e) {
+      un = fmaf(-cv[e], un, dv[e]);
+      o[e] = un;
+      Mh = fmaf(0.5f * (4 * (NC - 1) + e), 1.f - un, Mh);
+      umin = fminf(umin, un);
+    }
+    st_chunk(row, key, NC - 1, make_float4(o[0], o[1], o[2], 0.f));
+    tmem_wait_ld();
+    cq = cn;
+  }
+#pragma unroll 1
+  for (int c = NC - 2; c >= 0; --c) {
+    const float4 dq = ld_chunk(row, key, c);
+    float4 cn = tmem_ld4(taddr + 4 * max(c - 1, 0));
+    const float dv[4] = {dq.x, dq.y, dq.z, dq.w}, cv[4] = {cq.x, cq.y, cq.z, cq.w};
+    float o[4];
+    const float jb = 2.f * (float)c;  // j/2 of the chunk's first node
+#pragma unroll
+    for (int e = 3; e >= 0; --e) {
+      un = fmaf(-cv[e], un, dv[e]);
+      o[e] = un;
+      Mh = fmaf(jb + 0.5f * e, 1.f - un, Mh);
+      umin = fminf(umin, un);
+    }
+    st_chunk(row, key, c, make_float4(o[0], o[1], o[2], o[3]));
+    tmem_wait_ld();
+    cq = cn;
+  }
+  row[(((NC - 1) ^ key) << 2) | 3] = 2.f * DR * sqrtf(fmaxf(Mh * (1.f - umin), 0.f));
+  return un;
+}
+
+// #{k : xs[k] < x} over a sorted array padded with +inf to 2*top entries (top = power of two, 2*top-1 >= n)
+__device__ __forceinline__ int count_below(const float* xs, int top, float x) {
+  int c = 0;
+  for (int s = top; s > 0; s >>= 1)
+    if (xs[c + s - 1] < x) c += s;
+  return c;
+}
+
 struct LaneLoc {
   int chain, slot, q, valid;
 };
 
-__device__ __forceinline__ LaneLoc locate(const FlowShared& sh, int tile, int lane, int T, int P, int ntot) {
+template <class SH>
+__device__ __forceinline__ LaneLoc locate(const SH& sh, int tile, int lane, int T, int P, int ntot) {
   LaneLoc L;
   int fl = tile * WG_TILE + lane;
   L.valid = fl < ntot;
@@ -390,12 +519,15 @@ __device__ __noinline__ void flush_hits(const float* __restrict__ tile, const fl
   }
 }
 
-template <int VARIANT, int SYNC_ROUNDS>
-__global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_kernel(const Dev d, const FlowArgs a) {
+template <int VARIANT, int SYNC_ROUNDS, int WG_NWARP, int TC>
+__global__ void __launch_bounds__(WG_NWARP * 32, (VARIANT == 0 ? 16 : (VARIANT == 1 ? 12 : 20)) / WG_NWARP)
+    wg_flow_kernel(const Dev d, const FlowArgs a) {
+  static_assert(VARIANT != 2 || WG_NWARP == 4, "the TMEM scratch maps one warp per 32-lane quarter");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  FlowShared& sh = *reinterpret_cast<FlowShared*>(smem_raw);
+  typedef FlowShared<WG_NWARP, TC> Shared;
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int T = d.T, P = d.P, F = d.F;
-  float* bufs = reinterpret_cast<float*>(smem_raw + ((sizeof(FlowShared) + 127) / 128) * 128);
+  float* bufs = reinterpret_cast<float*>(smem_raw + hdr_bytes<WG_NWARP, TC>());
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / F, f = blockIdx.x % F;
@@ -414,7 +546,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
   float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;
   float* pmut0 = d.pmut + (size_t)bf * T * P * 4;
   float* pmut1 = pmut0 + (size_t)d.B * F * T * P * 4;
-  float* tile_base = bufs + (size_t)warp * (VARIANT == 0 ? 1 : 2) * WG_TILE * WG_NR;
+  float* tile_base = bufs + (size_t)warp * (VARIANT == 1 ? 2 : 1) * WG_TILE * WG_NR;
   float* row = tile_base + lane * WG_NR;
   float* cps = row + WG_TILE * WG_NR;  // variant 1: c' scratch row behind the warp's tile
   (void)cps;
@@ -447,13 +579,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
     sh.sum_ws[tid] = sh.sum_wd[tid] = sh.sum_yaw[tid] = sh.sum_pw[tid] = 0.f;
   }
   if (tid == 0) sh.base_sum = 0.f;
+  if (VARIANT == 2 && warp == 0) tmem_alloc(&sh.tmem_base);
+  for (int i = T + tid; i < 2 * TC; i += blockDim.x) sh.xs[i] = CUDART_INF_F;
   if (lane == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   int nstep = d.n_step[bf];
   uint32_t phase = 0;
+  if (VARIANT == 2) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  uint32_t taddr = 0;
+  if (VARIANT == 2) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    taddr = sh.tmem_base + ((uint32_t)(warp * 32) << 16);
+  }
   if (tid < T) {  // rank sort of the rotor-plane x positions (ties broken by index): xs ascending, ord = turbine
     const float x = sh.xr[tid];
     int rank = 0;
@@ -465,9 +605,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
     sh.ord[rank] = tid;
   }
   __syncthreads();
-  // sorted rotor-plane positions held across the lanes of every warp (T <= 64): range queries by ballot
-  const float xs_a = lane < T ? sh.xs[lane] : CUDART_INF_F;
-  const float xs_b = lane + 32 < T ? sh.xs[lane + 32] : CUDART_INF_F;
+  int xs_top = 1;
+  while (2 * xs_top - 1 < T) xs_top <<= 1;
   const float x_retire = xmax + MARGIN_D * d.D;
 
   for (int sub = 0; sub < nsteps; ++sub) {
@@ -502,7 +641,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
       }
       sh.count[tid] = cnt;
     }
-    for (int i = tid; i < WG_NWARP * WG_MAX_T; i += blockDim.x) {
+    for (int i = tid; i < WG_NWARP * TC; i += blockDim.x) {
       (&sh.acc_du[0][0])[i] = 0.f;
       (&sh.acc_dv[0][0])[i] = 0.f;
     }
@@ -546,15 +685,26 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
       const int nt = tile + WG_NWARP;
       if (nt < ntiles) {
         Ln = locate(sh, nt, lane, T, P, ntot);
-        if (Ln.valid)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + ((size_t)Ln.chain * P + Ln.slot) * WG_NR));
+        if (Ln.valid) {
+          const size_t st = (size_t)Ln.chain * P + Ln.slot;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + st * WG_NR));
+          if (lane == 0 || (Ln.slot & 7) == 0) {  // the station scalars: one 128-byte line per 8 slots
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st * 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st * 4));
+          }
+        }
       }
       const int key = Lc.slot & 7;
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
       if (Lc.valid) moved(pmc, pcc, ws, dt, xn, yn, zn, dx);
       mbar_wait(bar, phase);
       phase ^= 1u;
-      if (Lc.valid) {
+      if (VARIANT == 2) {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
+        const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
+        const float ucn = march_row_tmem(row, taddr, key, dx * rR, xt_mid, pcc.y);
+        if (Lc.valid)
+          *reinterpret_cast<float4*>(pm_new + ((size_t)Lc.chain * P + Lc.slot) * 4) = make_float4(xn, yn, zn, ucn);
+      } else if (Lc.valid) {
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
         const float ucn = VARIANT == 0 ? march_row_regs(row, key, dx * rR, xt_mid, pcc.y)
                                        : march_row_smem(row, cps, key, dx * rR, xt_mid, pcc.y);
@@ -570,69 +720,60 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
       {
         // older neighbour = flat index - 1 (same chain), younger = flat index + 1
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
-        const int co = __shfl_up_sync(full, Lc.chain, 1);
+        const int ch_o = __shfl_up_sync(full, Lc.chain, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        const int cy = __shfl_down_sync(full, Lc.chain, 1);
+        const int ch_y = __shfl_down_sync(full, Lc.chain, 1);
         const int vy_ = __shfl_down_sync(full, Lc.valid, 1);
         const bool has_o = Lc.valid && Lc.q > 0;
         const bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
-        if (has_o && (lane == 0 || co != Lc.chain)) {
+        if (has_o && (lane == 0 || ch_o != Lc.chain)) {
           int so = Lc.slot == 0 ? P - 1 : Lc.slot - 1;
           float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + so) * 4));
           float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + so) * 4));
           float dxx;
           moved(pm, pc, ws, dt, xo, yo, zo, dxx);
         }
-        if (has_y && (lane == 31 || !vy_ || cy != Lc.chain)) {
+        if (has_y && (lane == 31 || !vy_ || ch_y != Lc.chain)) {
           int sy = Lc.slot == P - 1 ? 0 : Lc.slot + 1;
           float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + sy) * 4));
           float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + sy) * 4));
           float dxx;
           moved(pm, pc, ws, dt, xy, yy, zy, dxx);
         }
-        if (!has_o) { xo = xn; yo = yn; zo = zn; }  // degenerate intervals never bracket anything
-        if (!has_y) { xy = xn; yy = yn; zy = zn; }
-        // x-range touched by this tile (warp-uniform): only rotor planes inside it can be bracketed
-        float lo = Lc.valid ? fminf(xn, fminf(xo, xy)) : CUDART_INF_F;
-        float hi = Lc.valid ? fmaxf(xn, fmaxf(xo, xy)) : -CUDART_INF_F;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          lo = fminf(lo, __shfl_xor_sync(full, lo, o));
-          hi = fmaxf(hi, __shfl_xor_sync(full, hi, o));
-        }
-        // sorted rotor planes with lo <= x < hi: [k0, k1)
-        const int k0 = __popc(__ballot_sync(full, xs_a < lo)) + __popc(__ballot_sync(full, xs_b < lo));
-        const int k1 = __popc(__ballot_sync(full, xs_a < hi)) + __popc(__ballot_sync(full, xs_b < hi));
+        // Rotor planes bracketed by this station and its age neighbours: with c(x) = #{k : xs[k] < x} over the sorted
+        // plane positions, plane k lies in [x1, x2) iff c(x1) <= k < c(x2).  Interval A = [self (younger end), older
+        // neighbour), interval B = [younger neighbour, self (older end)); an inverted pair counts with sign -1
+        // (oracle/dwm_numpy.py:353-356).  Every lane handles its own row for both of its intervals.
+        const int cn = count_below(sh.xs, xs_top, xn);
+        const int co = has_o ? count_below(sh.xs, xs_top, xo) : cn;
+        const int cy = has_y ? count_below(sh.xs, xs_top, xy) : cn;
+        const int a_lo = min(cn, co), nA = abs(cn - co), b_lo = min(cn, cy), nB = abs(cn - cy);
+        const int nmax = __reduce_max_sync(full, max(nA, nB));
         const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
         const int rowkey = lane | (key << 8);
+        const float rdA = rcp_fast(xo - xn), rdB = rcp_fast(xn - xy);
         int nh = 0;
-        for (int k = k0; k < k1; ++k) {
-          const float xj = sh.xs[k];
-          const int j = sh.ord[k];
-          // interval A: [self (younger end), older neighbour); interval B: [younger neighbour, self (older end)).
-          // sign +1 for the regular downstream-ordered pair, -1 if the pair is inverted (oracle/dwm_numpy.py:353-356)
-          const bool pn = xn <= xj, po = xo <= xj, py = xy <= xj;
-          const bool mine = Lc.valid && j != Lc.chain;
-          const bool hitA = mine && (pn != po), hitB = mine && (py != pn);
+        for (int it = 0; it < nmax; ++it) {
+          const int kA = a_lo + it, kB = b_lo + it;
+          const int jA = it < nA ? sh.ord[kA] : Lc.chain, jB = it < nB ? sh.ord[kB] : Lc.chain;
+          const bool hitA = jA != Lc.chain, hitB = jB != Lc.chain;
           const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
-          if ((mA | mB) == 0u) continue;
-          const float yrj = sh.yr[j];
           if (hitA) {
-            const float w = (xj - xn) * rcp_fast(xo - xn);
-            const float wg = pn ? 1.f - w : w - 1.f;
+            const float w = (sh.xs[kA] - xn) * rdA;
+            const float wg = kA >= cn ? 1.f - w : w - 1.f;
             const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
             const int p = nh + __popc(mA & lt);
-            ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
-            hb[p] = make_int2(rowkey, j);
+            ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
+            hb[p] = make_int2(rowkey, jA);
           }
           nh += __popc(mA);
           if (hitB) {
-            const float w = (xj - xy) * rcp_fast(xn - xy);
-            const float wg = py ? w : -w;
+            const float w = (sh.xs[kB] - xy) * rdB;
+            const float wg = kB >= cy ? w : -w;
             const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
             const int p = nh + __popc(mB & lt);
-            ha[p] = make_float4(wg * u0cg, wg * u0sg, (yrj - yc) * rR, (d.zh - zc) * rR);
-            hb[p] = make_int2(rowkey, j);
+            ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
+            hb[p] = make_int2(rowkey, jB);
           }
           nh += __popc(mB);
           if (nh > WG_HIT_CAP - 64) {
@@ -754,10 +895,14 @@ __global__ void __launch_bounds__(WG_NWARP * 32, VARIANT == 0 ? 4 : 3) wg_flow_k
     d.n_step[bf] = nstep;
     if (a.mode == FLOW_STEP && f == 1) d.base_pow_mean[b] = sh.base_sum / (float)nsteps;
   }
+  if (VARIANT == 2 && warp == 0) {  // every warp's last TMEM access precedes the substep loop's closing barrier
+    __syncwarp();
+    tmem_dealloc(sh.tmem_base);
+  }
 }
 
-// Variant 0 (default): c' in registers, unrolled march, 4 CTAs/SM.  Variant 1 (WG_FLOW_VARIANT=1): c' in shared
-// memory, rolled march.  WG_FLOW_SYNC=1: the CTA's warps start every tile round together (instruction-cache sharing).
+// WG_FLOW_VARIANT: 0 = c' in registers, unrolled march; 1 = c' in shared memory, rolled march; 2 = c' in TMEM,
+// rolled march.  WG_FLOW_SYNC=1: the CTA's warps start every tile round together (instruction-cache sharing).
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0] >= '0' && e[0] <= '9') ? atoi(e) : dflt;
@@ -765,21 +910,31 @@ static int env_int(const char* name, int dflt) {
 
 typedef void (*flow_fn)(const Dev, const FlowArgs);
 
-cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  static const int v = env_int("WG_FLOW_VARIANT", 0) ? 1 : 0;
-  static const int sync = env_int("WG_FLOW_SYNC", 1) ? 1 : 0;
-  static const flow_fn fns[2][2] = {{wg_flow_kernel<0, 0>, wg_flow_kernel<0, 1>},
-                                    {wg_flow_kernel<1, 0>, wg_flow_kernel<1, 1>}};
-  const flow_fn fn = fns[v][sync];
-  const size_t smem = flow_smem_bytes(d.T, v == 0 ? 1 : 2);
+template <int V, int SY, int NW, int TC>
+static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
+  const flow_fn fn = wg_flow_kernel<V, SY, NW, TC>;
+  const size_t smem = hdr_bytes<NW, TC>() + (size_t)NW * (V == 1 ? 2 : 1) * WG_TILE * WG_ROW_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  fn<<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  fn<<<d.B * d.F, NW * 32, smem, s>>>(d, a);
   return cudaGetLastError();
+}
+
+template <int V, int SY>
+static cudaError_t launch_tc(const Dev& d, const FlowArgs& a, cudaStream_t s) {
+  return d.T <= 16 ? launch_as<V, SY, 4, 16>(d, a, s) : launch_as<V, SY, 4, WG_MAX_T>(d, a, s);
+}
+
+cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
+  static const int v = env_int("WG_FLOW_VARIANT", 2);
+  static const int sync = env_int("WG_FLOW_SYNC", 1) ? 1 : 0;
+  if (v == 0) return sync ? launch_tc<0, 1>(d, a, s) : launch_tc<0, 0>(d, a, s);
+  if (v == 1) return sync ? launch_tc<1, 1>(d, a, s) : launch_tc<1, 0>(d, a, s);
+  return sync ? launch_tc<2, 1>(d, a, s) : launch_tc<2, 0>(d, a, s);
 }
 
 }  // namespace wg

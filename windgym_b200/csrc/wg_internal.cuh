@@ -100,7 +100,6 @@ struct ResetDevArgs {
 };
 
 void set_rotor_points(const float* qy, const float* qz);
-size_t flow_smem_bytes(int T, int n_stage);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
