@@ -98,6 +98,8 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.spin = at<int>(state, h, "spin");
   d.xr = at<float>(state, h, "xr");
   d.yr = at<float>(state, h, "yr");
+  d.xs_sorted = at<float>(state, h, "xs_sorted");
+  d.ord_sorted = at<int>(state, h, "ord_sorted");
   d.meas = at<float>(state, h, "meas");
   d.base_pow_mean = at<float>(state, h, "base_pow_mean");
   d.old_yaw = at<float>(state, h, "old_yaw");
@@ -293,6 +295,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
     add_field(h, n, 1, {B});
   add_field(h, "xr", 0, {B, T});
   add_field(h, "yr", 0, {B, T});
+  add_field(h, "xs_sorted", 0, {B, T});
+  add_field(h, "ord_sorted", 1, {B, T});
   add_field(h, "meas", 0, {B, 4, T});
   add_field(h, "old_yaw", 0, {B, T});
   add_field(h, "rings", 0, {B, off});

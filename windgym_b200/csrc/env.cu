@@ -222,6 +222,17 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
     d.old_yaw[b * T + tid] = yaw0;
     for (int cc = 0; cc < 4; ++cc) d.meas[(b * 4 + cc) * T + tid] = 0.f;
   }
+  __syncthreads();
+  if (tid < T) {  // rotor planes sorted by x (ties by index): the flow kernel's bracket search runs on this order
+    const float x = d.xr[b * T + tid];
+    int rank = 0;
+    for (int t = 0; t < T; ++t) {
+      const float xt = d.xr[b * T + t];
+      rank += (xt < x || (xt == x && t < tid)) ? 1 : 0;
+    }
+    d.xs_sorted[b * T + rank] = x;
+    d.ord_sorted[b * T + rank] = tid;
+  }
   if (tid == 0) {
     double xm = -1e300;
     for (int t = 0; t < T; ++t) xm = fmax(xm, (d.x_pos[t] - mx) * c + (d.y_pos[t] - my) * s);

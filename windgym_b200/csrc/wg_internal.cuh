@@ -70,6 +70,8 @@ struct Dev {
   float *ws, *ti, *wd, *rated, *xmax;   // [B]
   int *k_emit, *time_max, *timestep, *flags, *n_push, *n_fp, *n_bp, *spin;  // [B]
   float *xr, *yr;         // [B,T]
+  float *xs_sorted;       // [B,T] rotor-plane x ascending (ties by turbine index); int *ord_sorted: turbine of each
+  int *ord_sorted;        // [B,T]
   float *meas;            // [B,4,T] substep means ws, wd, yaw, power
   float *base_pow_mean;   // [B]
   float *old_yaw;         // [B,T]
