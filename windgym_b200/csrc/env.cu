@@ -74,55 +74,93 @@ __device__ float calc_ti(Get get, int L) {
   return (float)(sqrt(var) / U);
 }
 
-__global__ void __launch_bounds__(128) wg_finish_kernel(const Dev d, const FinishArgs a) {
-  const int b = blockIdx.x, tid = threadIdx.x, T = d.T;
+// One WARP per env (4 envs per CTA): every phase is a lane-strided loop, phases are separated by __syncwarp.
+// STAGE = true: the env's measurement rings and power deques are staged in shared memory first (one coalesced
+// read instead of dependent global loads inside the serial window sums); pushes go to both copies.
+#define WG_FIN_WARPS 4
+template <bool STAGE>
+__global__ void __launch_bounds__(WG_FIN_WARPS * 32) wg_finish_kernel(const Dev d, const FinishArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
+  const int b = blockIdx.x * WG_FIN_WARPS + warp;
+  if (b >= d.B) return;
   if (a.mask && !a.mask[b]) return;
-  __shared__ float s_val[4][WG_MAX_T];
-  float* rings = d.rings + (size_t)b * d.ring_floats;
+  extern __shared__ float s_dyn[];
+  __shared__ float s_vals[WG_FIN_WARPS][4][WG_MAX_T];
+  float (*s_val)[WG_MAX_T] = s_vals[warp];
+  float* g_rings = d.rings + (size_t)b * d.ring_floats;
+  float* g_fp = d.fp_ring + (size_t)b * d.power_avg;
+  float* g_bp = d.bp_ring + (size_t)b * d.power_avg;
+  const int per_env = d.ring_floats + 2 * d.power_avg;
+  float* rings = STAGE ? s_dyn + (size_t)warp * per_env : g_rings;
+  float* fp = STAGE ? rings + d.ring_floats : g_fp;
+  float* bp = STAGE ? fp + d.power_avg : g_bp;
+  if (STAGE) {
+    for (int i = lane; i < d.ring_floats; i += 32) rings[i] = g_rings[i];
+    for (int i = lane; i < d.power_avg; i += 32) { fp[i] = g_fp[i]; bp[i] = g_bp[i]; }
+  }
   int np = d.n_push[b];
-
-  if (a.flags & FIN_PUSH_MES) {
-    if (tid < T) {
+  int nfp_tot = d.n_fp[b], nbp_tot = d.n_bp[b];
+  if (a.flags & (FIN_PUSH_MES | FIN_PUSH_FP))
+    for (int t = lane; t < T; t += 32) {
       const float* src[4] = {a.in_ws, a.in_wd, a.in_yaw, a.in_power};
 #pragma unroll
+      for (int c = 0; c < 4; ++c)
+        s_val[c][t] = (a.flags & FIN_MEAS_FROM_ARGS) ? src[c][b * T + t] : d.meas[(b * 4 + c) * T + t];
+    }
+  __syncwarp();
+
+  if (a.flags & FIN_PUSH_FP) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977): noise-free means
+    if (lane == 0) {
+      auto gp = [&](int k) { return (double)s_val[3][k]; };
+      const float v = (float)pairwise_sum(gp, 0, T);
+      fp[nfp_tot % d.power_avg] = v;
+      if (STAGE) g_fp[nfp_tot % d.power_avg] = v;
+      d.n_fp[b] = nfp_tot + 1;
+    }
+    nfp_tot += 1;
+  }
+  if (a.flags & FIN_PUSH_BP) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
+    if (lane == 0) {
+      const float v = d.base_pow_mean[b];
+      bp[nbp_tot % d.power_avg] = v;
+      if (STAGE) g_bp[nbp_tot % d.power_avg] = v;
+      d.n_bp[b] = nbp_tot + 1;
+    }
+    nbp_tot += 1;
+  }
+  __syncwarp();  // s_val is overwritten with the noisy values below
+
+  if (a.flags & FIN_PUSH_MES) {
+    for (int t = lane; t < T; t += 32) {
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float v = (a.flags & FIN_MEAS_FROM_ARGS) ? src[c][b * T + tid] : d.meas[(b * 4 + c) * T + tid];
-        if (d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, tid);
-        s_val[c][tid] = v;
-        const int r = c * T + tid;
-        rings[d.ring_off[r] + np % d.ch_H[c]] = v;  // deque.append (MesClass.py:66-68, :580-586)
+        float v = s_val[c][t];
+        if (d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, t);
+        s_val[c][t] = v;
+        const int r = c * T + t;
+        const int o = d.ring_off[r] + np % d.ch_H[c];
+        rings[o] = v;  // deque.append (MesClass.py:66-68, :580-586)
+        if (STAGE) g_rings[o] = v;
       }
     }
-    __syncthreads();
-    if (tid == 0) {  // farm-level rings: mean ws, mean wd, sum power (MesClass.py:589-591)
-      auto gw = [&](int k) { return (double)s_val[0][k]; };
-      auto gd = [&](int k) { return (double)s_val[1][k]; };
-      auto gp = [&](int k) { return (double)s_val[3][k]; };
-      rings[d.ring_off[4 * T + 0] + np % d.ch_H[0]] = (float)(pairwise_sum(gw, 0, T) / T);
-      rings[d.ring_off[4 * T + 1] + np % d.ch_H[1]] = (float)(pairwise_sum(gd, 0, T) / T);
-      rings[d.ring_off[4 * T + 2] + np % d.ch_H[3]] = (float)pairwise_sum(gp, 0, T);
-      d.n_push[b] = np + 1;
+    __syncwarp();
+    if (lane < 3) {  // farm-level rings: mean ws, mean wd, sum power (MesClass.py:589-591)
+      const int c = lane == 2 ? 3 : lane;
+      auto g = [&](int k) { return (double)s_val[c][k]; };
+      const double sum = pairwise_sum(g, 0, T);
+      const float v = (float)(lane == 2 ? sum : sum / T);
+      const int o = d.ring_off[4 * T + lane] + np % d.ch_H[c];
+      rings[o] = v;
+      if (STAGE) g_rings[o] = v;
     }
+    if (lane == 0) d.n_push[b] = np + 1;
     np += 1;
   }
-  if (tid == 0) {
-    if (a.flags & FIN_PUSH_FP) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977)
-      auto gp = [&](int k) { return (double)d.meas[(b * 4 + 3) * T + k]; };
-      const int n = d.n_fp[b];
-      d.fp_ring[(size_t)b * d.power_avg + n % d.power_avg] = (float)pairwise_sum(gp, 0, T);
-      d.n_fp[b] = n + 1;
-    }
-    if (a.flags & FIN_PUSH_BP) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
-      const int n = d.n_bp[b];
-      d.bp_ring[(size_t)b * d.power_avg + n % d.power_avg] = d.base_pow_mean[b];
-      d.n_bp[b] = n + 1;
-    }
-  }
-  __syncthreads();
+  __syncwarp();
 
   if (a.flags & FIN_OBS) {  // farm_mes.get_measurements(scaled=True) + clip (MesClass.py:679-703, Wind_Farm_Env.py:513-520)
     const int n_out = d.obs_rows * d.obs_dim;
-    for (int o = tid; o < n_out; o += blockDim.x) {
+    for (int o = lane; o < n_out; o += 32) {
       const ObsDesc ds = d.obs_desc[o];
       float val = 0.f;
       if (np > 0) {
@@ -157,11 +195,9 @@ __global__ void __launch_bounds__(128) wg_finish_kernel(const Dev d, const Finis
     }
   }
 
-  if ((a.flags & FIN_REWARD) && tid == 0) {
+  if ((a.flags & FIN_REWARD) && lane == 0) {
     const int PA = d.power_avg;
-    const int nfp = min(d.n_fp[b], PA), nbp = min(d.n_bp[b], PA);
-    const float* fp = d.fp_ring + (size_t)b * PA;
-    const float* bp = d.bp_ring + (size_t)b * PA;
+    const int nfp = min(nfp_tot, PA), nbp = min(nbp_tot, PA);
     bool nan_seen = false;
     double sfp = 0.0, sbp = 0.0;
     for (int k = 0; k < nfp; ++k) { sfp += fp[k]; nan_seen |= isnan(fp[k]); }
@@ -173,7 +209,7 @@ __global__ void __launch_bounds__(128) wg_finish_kernel(const Dev d, const Finis
     } else if (d.power_reward == 2) {
       rew = (sfp / nfp) / T / (double)d.rated[b];
     } else if (d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
-      const int ws_ = PA / 10, ntot = d.n_fp[b];
+      const int ws_ = PA / 10, ntot = nfp_tot;
       auto lg = [&](int k) { return (double)fp[(ntot - nfp + k) % PA]; };
       double latest = 0.0, oldest = 0.0;
       int nl = 0, no = 0;
@@ -245,7 +281,19 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
 }
 
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
-  wg_finish_kernel<<<d.B, 128, 0, s>>>(d, a);
+  const size_t smem = sizeof(float) * WG_FIN_WARPS * ((size_t)d.ring_floats + 2 * (size_t)d.power_avg);
+  const int grid = (d.B + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
+  if (smem <= 100 * 1024) {
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = smem;
+    }
+    wg_finish_kernel<true><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
+  } else {
+    wg_finish_kernel<false><<<grid, WG_FIN_WARPS * 32, 0, s>>>(d, a);
+  }
   return cudaGetLastError();
 }
 
