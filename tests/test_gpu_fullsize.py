@@ -1,0 +1,107 @@
+"""GPU parity at BASELINE.json's full sizes: cfg 2 (4x4 farm, 4096 envs) and cfg 4 (8x8 farm, 1024 envs).
+
+The oracle cannot run thousands of envs in seconds, so the full-size checks are
+  * a handful of envs of the big batch against the oracle on the same conditions (power 1e-4 rel, obs 2e-5 abs),
+  * size-independent properties: batch independence (an env gives bit-identical results alone and inside the
+    4096-env batch), duplicated envs agree bit for bit, launch-to-launch determinism, physical bounds
+    (0 <= P <= rated curve maximum, free-stream power at the most upstream rotor), no device error flags.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_rollout, small_config
+
+pytestmark = pytest.mark.gpu
+
+POWER_RTOL, OBS_ATOL = 1e-4, 2e-5
+
+
+def _conditions(B, T, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.uniform(7, 15, B), rng.uniform(0.02, 0.15, B), rng.uniform(255, 285, B),
+            rng.uniform(-15, 15, (B, T)))
+
+
+def _rollout(cfg, ws, ti, wd, yaw0, acts, **kw):
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    B, T = yaw0.shape
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", **kw)
+    obs0, _ = env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    out = dict(obs0=obs0.cpu().numpy().copy(), obs=[], reward=[], power=[], u=[])
+    for a in acts:
+        o, r, _, tr, info = env.step(torch.as_tensor(a))
+        out["obs"].append(o.cpu().numpy().copy())
+        out["reward"].append(r.cpu().numpy().copy())
+        out["power"].append(info["Power pr turbine agent"].cpu().numpy().copy())
+        out["u"].append(env.state["u"][:, 0].cpu().numpy().copy())
+    env.check_flags()
+    live = int(env.state["count"].sum().item())
+    xr = env.state["xr"].cpu().numpy().copy()
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return {k: np.array(v) for k, v in out.items()}, live, xr
+
+
+def test_cfg2_4096_envs_vs_oracle_and_batch_independence(built_lib):
+    nx = ny = 4
+    T, B, steps = 16, 4096, 3
+    cfg = small_config(nx, ny, reward="Power_avg", action="wind")
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=2024)
+    # envs 1 and 4095 are copies of env 0: identical inputs must give identical bits anywhere in the batch
+    for k in (1, B - 1):
+        ws[k], ti[k], wd[k], yaw0[k] = ws[0], ti[0], wd[0], yaw0[0]
+    acts = np.random.default_rng(7).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    acts[:, 1] = acts[:, 0]
+    acts[:, B - 1] = acts[:, 0]
+    big, live, xr = _rollout(cfg, ws, ti, wd, yaw0, acts)
+    assert live > 500 * B, "wake chains should be developed after reset"
+    # --- duplicates
+    for k in (1, B - 1):
+        assert np.array_equal(big["power"][:, k], big["power"][:, 0])
+        assert np.array_equal(big["obs"][:, k], big["obs"][:, 0])
+    # --- physical bounds on the whole batch
+    assert np.isfinite(big["power"]).all() and np.isfinite(big["obs"]).all() and np.isfinite(big["reward"]).all()
+    assert big["power"].min() >= 0.0 and big["power"].max() <= 2.0e6 + 1.0
+    assert np.abs(big["obs"]).max() <= 1.0
+    # the most upstream rotor of every env sees the free stream: u == ws (no wake reaches it)
+    up = xr.argmin(axis=1)
+    u_up = big["u"][-1][np.arange(B), up]
+    assert np.allclose(u_up, ws, rtol=1e-6)
+    # --- a few envs against the oracle
+    sel = [0, 17, 2048, 4094]
+    ref = oracle_rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts[:, sel])
+    for i, b in enumerate(sel):
+        rel = np.abs(big["power"][:, b] - ref["power"][i]) / np.maximum(ref["power"][i], 1.0)
+        assert rel.max() < POWER_RTOL, f"env {b}: power rel err {rel.max():.3e}"
+        assert np.allclose(big["obs0"][b], ref["obs0"][i], atol=OBS_ATOL)
+        assert np.allclose(big["obs"][:, b], ref["obs"][i], atol=OBS_ATOL)
+        assert np.allclose(big["reward"][:, b], ref["reward"][i], rtol=2e-4, atol=2e-5)
+    # --- batch independence + determinism: the same envs alone in a small batch, bit for bit
+    small, _, _ = _rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts[:, sel])
+    assert np.array_equal(small["power"], big["power"][:, sel])
+    assert np.array_equal(small["obs"], big["obs"][:, sel])
+    assert np.array_equal(small["reward"], big["reward"][:, sel])
+
+
+def test_cfg4_64_turbines_1024_envs_vs_oracle(built_lib):
+    nx = ny = 8
+    T, B, steps = 64, 1024, 2
+    cfg = small_config(nx, ny, reward="Power_avg", action="yaw")
+    cfg["wind"]["ws_min"], cfg["wind"]["ws_max"] = 11, 15   # keeps the oracle's spin-up short
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=64)
+    ws = np.clip(ws, 11, 15)
+    ws[1], ti[1], wd[1], yaw0[1] = ws[0], ti[0], wd[0], yaw0[0]
+    acts = np.random.default_rng(8).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    acts[:, 1] = acts[:, 0]
+    big, live, xr = _rollout(cfg, ws, ti, wd, yaw0, acts, fill_window=2)
+    assert np.array_equal(big["power"][:, 1], big["power"][:, 0])
+    assert np.isfinite(big["power"]).all() and big["power"].min() >= 0.0 and big["power"].max() <= 2.0e6 + 1.0
+    up = xr.argmin(axis=1)
+    assert np.allclose(big["u"][-1][np.arange(B), up], ws, rtol=1e-6)
+    sel = [0]
+    ref = oracle_rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts[:, sel], fill_window=2)
+    rel = np.abs(big["power"][:, 0] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
+    assert rel.max() < POWER_RTOL, f"power rel err {rel.max():.3e}"
+    assert np.allclose(big["obs"][:, 0], ref["obs"][0], atol=OBS_ATOL)

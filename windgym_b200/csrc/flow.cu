@@ -41,16 +41,16 @@ namespace wg {
 
 __constant__ float c_qy[WG_NQ];
 __constant__ float c_qz[WG_NQ];
-// per-node constants of the radial grid r_j = j dr, two nodes per entry: {1/(2j), j/2, 1/(2(j+1)), (j+1)/2}
-__constant__ float4 c_node2[WG_NR / 2];
+// rho_j = j / (j + 1) of the radial grid r_j = j dr, four nodes per entry (see WG_NODE_FWD)
+__constant__ float4 c_rho4[WG_NR / 4];
 
 void set_rotor_points(const float* qy, const float* qz) {
   cudaMemcpyToSymbol(c_qy, qy, sizeof(float) * WG_NQ);
   cudaMemcpyToSymbol(c_qz, qz, sizeof(float) * WG_NQ);
-  float4 nd[WG_NR / 2];
-  for (int j = 0; j < WG_NR; j += 2)
-    nd[j / 2] = make_float4(j ? 1.f / (2.f * j) : 0.f, 0.5f * j, 1.f / (2.f * (j + 1)), 0.5f * (j + 1));
-  cudaMemcpyToSymbol(c_node2, nd, sizeof(nd));
+  float4 nd[WG_NR / 4];
+  for (int j = 0; j < WG_NR; j += 4)
+    nd[j / 4] = make_float4(j / (j + 1.f), (j + 1) / (j + 2.f), (j + 2) / (j + 3.f), (j + 3) / (j + 4.f));
+  cudaMemcpyToSymbol(c_rho4, nd, sizeof(nd));
 }
 
 // Per-CTA bookkeeping in front of the tile buffers.  TC = turbine capacity of the tables (16 or WG_MAX_T: small
@@ -226,9 +226,11 @@ __device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws
 // With h = 1/(2j), N = nu/dr^2:
 //   lap_j dr^2 = U_{j+1} + U_{j-1} - 2 U_j + h (U_{j+1} - U_{j-1}),  Vd_j = nu Vh_j / (2 dr) = -N h I_j,
 //   sub-diagonal -a_j = -(N - N h (1 + I_j)), super-diagonal c_j = -N - N h (1 + I_j), diagonal U_j/dx + 2N.
-// The sweep carries W = 1 + I: lap_j dr^2 + h dU (I + rgh) = (su - 2 U_j) + h dU (W + rgh).
-// Node j of the forward sweep; h = 1/(2j), jh = j/2.
-#define WG_NODE_FWD(uj, up1, um, h, jh, AXIS)                                           \
+// The sweep carries Z = h (1 + I) instead of I: with h_j j/2 = 1/4 and rho_j = h_{j+1}/h_j = j/(j+1),
+//   G_j = (lap_j dr^2 + h dU (I + rgh)) / den = ((su - 2 U_j) + dU Zp_j) / den,   Zp_j = h_j (1 + I_{j-1} + rgh_{j-1}),
+//   Z_j = Zp_j + G_j/4,  Zp_{j+1} = rho_j (Z_j + G_j/4),  a_j = N - N Z_j,  c_j = -N - N Z_j   (Zp_1 = 1/2),
+// so the only per-node grid constant is rho_j.
+#define WG_NODE_FWD(uj, up1, um, rho, AXIS)                                             \
   {                                                                                     \
     const float ui = (uj) * idx;                                                        \
     float bb = ui + N2, dd = ui * (uj), a = 0.f, cc = -2.f * N2;                        \
@@ -236,16 +238,13 @@ __device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws
       bb += N2; /* axis node: diagonal U_0/dx + 4N, super-diagonal -4N, no sub-diagonal */ \
     } else {                                                                            \
       const float du = (up1) - (um), su = (up1) + (um);                                 \
-      const float hd = (h) * du;                                                        \
-      const float t2 = fmaf(-2.f, (uj), su);      /* lap dr^2 - hd */                   \
-      const float Wp = W + rgh;                   /* W = 1 + I */                       \
+      const float t2 = fmaf(-2.f, (uj), su);                                            \
       const float den = fmaf(-0.25f, du, (uj));                                         \
-      const float G = fmaf(hd, Wp, t2) * rcp_fast(den);                                 \
-      rgh = (jh) * G;                                                                   \
-      W = Wp + rgh;                                                                     \
-      const float q = (h) * W;                    /* h (1 + I) */                       \
-      a = fmaf(-N, q, N);                                                               \
-      cc = fmaf(-N, q, -N);                                                             \
+      const float G = fmaf(du, Zp, t2) * rcp_fast(den);                                 \
+      const float Z = fmaf(0.25f, G, Zp);                                               \
+      a = fmaf(-N, Z, N);                                                               \
+      cc = fmaf(-N, Z, -N);                                                             \
+      Zp = (rho) * fmaf(0.25f, G, Z);                                                   \
     }                                                                                   \
     const float m = rcp_fast(fmaf(a, cpm, bb));                                         \
     cpm = cc * m;                                                                       \
@@ -264,13 +263,13 @@ __device__ __forceinline__ float march_row_tmem(uint32_t rowk, uint32_t taddr, f
   const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
   const float idx = 1.f / fmaxf(dxt, DXT_MIN);
   const float N = nu * IDR2, N2 = 2.f * N;
-  float W = 1.f, rgh = 0.f, cpm = 0.f, dpm = 0.f, um = 0.f;
+  float Zp = 0.5f, cpm = 0.f, dpm = 0.f, um = 0.f;
   {  // chunk 0
     const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
     float dout[4], cout[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      WG_NODE_FWD(uu[e], uu[e + 1], um, (e ? 1.f / (2.f * e) : 0.f), 0.5f * e, e == 0)
+      WG_NODE_FWD(uu[e], uu[e + 1], um, e / (e + 1.f), e == 0)
       cout[e] = cpm;
       dout[e] = dpm;
       um = uu[e];
@@ -286,17 +285,14 @@ __device__ __forceinline__ float march_row_tmem(uint32_t rowk, uint32_t taddr, f
     const float4 n2 = lds4(rowk ^ ((uint32_t)(c + 2) << 4));
     const float uu[9] = {cur.x, cur.y, cur.z, cur.w, n1.x, n1.y, n1.z, n1.w, n2.x};
     float dout[8], cout[8];
+    const float4 r0 = c_rho4[c], r1 = c_rho4[c + 1];
+    const float rho[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-    for (int e = 0; e < 8; e += 2) {
-      const float4 nd = c_node2[2 * c + (e >> 1)];
-      WG_NODE_FWD(uu[e], uu[e + 1], um, nd.x, nd.y, false)
+    for (int e = 0; e < 8; ++e) {
+      WG_NODE_FWD(uu[e], uu[e + 1], um, rho[e], false)
       cout[e] = cpm;
       dout[e] = dpm;
       um = uu[e];
-      WG_NODE_FWD(uu[e + 1], uu[e + 2], um, nd.z, nd.w, false)
-      cout[e + 1] = cpm;
-      dout[e + 1] = dpm;
-      um = uu[e + 1];
     }
     sts4(a0, dout[0], dout[1], dout[2], dout[3]);
     sts4(a1, dout[4], dout[5], dout[6], dout[7]);
@@ -310,7 +306,7 @@ __device__ __forceinline__ float march_row_tmem(uint32_t rowk, uint32_t taddr, f
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
       const int j = 4 * (NC - 1) + e;
-      WG_NODE_FWD(uu[e], uu[e + 1], um, 1.f / (2.f * j), 0.5f * j, false)
+      WG_NODE_FWD(uu[e], uu[e + 1], um, j / (j + 1.f), false)
       cout[e] = cpm;
       dout[e] = dpm;
       um = uu[e];
