@@ -85,3 +85,41 @@ def test_gather_is_identity_without_process_group():
     x = torch.arange(6.0).reshape(3, 2)
     assert gather_env_stats(x, 3) is x
     assert max_over_ranks(3.5, "cpu") == 3.5
+
+
+def _eval_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from tests.fake_vec_env import FakeVecEnv
+        from windgym_b200.agents import ConstantAgent
+        from windgym_b200.evaluate import eval_batched
+        wss, wds = [8.0, 10.0, 12.0], [265, 270, 275]          # 9 conditions over 2 ranks: 5 + 4
+        lo, hi = shard_range(9, rank, world)
+        env = FakeVecEnv(hi - lo, n_turb=3, eval_mode=True)
+        ds = eval_batched(env, ConstantAgent([-10, 20, 0]), wss, wds, [0.05], t_sim=5)
+        q.put((rank, ds["powerT_a"], ds.coords["time0"]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_eval_batched_sharded_over_two_ranks_equals_single_rank():
+    """f-2 on N>1: conditions sharded across ranks, ONE gather assembles the reference-shaped dataset on every rank."""
+    from tests.fake_vec_env import FakeVecEnv
+    from windgym_b200.agents import ConstantAgent
+    from windgym_b200.evaluate import eval_batched
+    single = eval_batched(FakeVecEnv(9, n_turb=3, eval_mode=True), ConstantAgent([-10, 20, 0]), [8.0, 10.0, 12.0],
+                          [265, 270, 275], [0.05], t_sim=5)
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, pT, t0 in res:
+        assert np.array_equal(pT, single["powerT_a"]) and np.array_equal(t0, single.coords["time0"])

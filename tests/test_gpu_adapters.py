@@ -1,0 +1,104 @@
+"""GPU: the f-2 / f-3 rows on the CUDA backend -- vector adapters with masked auto-reset, the batched evaluation
+against the single-env FarmEval facade loop (the reference's eval_single_fast pattern) and the oracle, an SB3-style
+MLP policy rolled out on the device."""
+import numpy as np
+import pytest
+
+from tests.helpers import oracle_rollout, small_config
+
+pytestmark = pytest.mark.gpu
+
+
+def test_vector_env_autoreset_matches_fresh_reset(built_lib):
+    import torch
+    from windgym_b200 import GymVectorEnv, RecordEpisodeVals, V80, VecWindFarmEnv
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    B, T = 4, 2
+    # n_passthrough tiny -> time_max = int(dist/ws * n_pass) is a handful of steps, different per env
+    env = RecordEpisodeVals(GymVectorEnv(V80(), B, config=cfg, n_passthrough=0.2, seed=5, device="cuda:0"))
+    obs, infos = env.reset(seed=5)
+    v = env.env.venv
+    tmax = v.time_max.copy()
+    assert obs.shape == (B, 4) and obs.dtype == np.float32 and (tmax > 0).all() and len(set(tmax.tolist())) > 1
+    first_done = None
+    for k in range(int(tmax.max()) + 3):
+        ws_before = v.ws.copy()
+        obs, r, term, trunc, infos = env.step(np.zeros((B, T), dtype=np.float32))
+        assert np.isfinite(obs).all() and np.abs(obs).max() <= 1.0 and not term.any()
+        assert np.array_equal(trunc, k >= tmax) or first_done is not None
+        if trunc.any() and first_done is None:
+            first_done = (k, trunc.copy())
+            assert np.array_equal(infos["_final_observation"], trunc)
+            ts = v.state["timestep"].cpu().numpy()
+            assert (ts[trunc] == 0).all() and (ts[~trunc] == k + 1).all()
+            # finished envs drew new conditions, the others kept theirs
+            assert (v.ws[trunc] != ws_before[trunc]).all() and (v.ws[~trunc] == ws_before[~trunc]).all()
+            # the auto-reset observation equals a fresh env reset onto the same conditions
+            fresh = VecWindFarmEnv(V80(), B, config=cfg, n_passthrough=0.2, device="cuda:0")
+            yaw_now = v.state["yaw"][:, 0].cpu().numpy()
+            f_obs, _ = fresh.reset(wind=(v.ws, v.ti, v.wd), yaw0=yaw_now)
+            assert np.array_equal(f_obs.cpu().numpy()[trunc], obs[trunc])
+            fresh.close()
+    assert first_done is not None and len(env.mean_power_queue) >= B
+    assert all(p > 0 for p in env.mean_power_queue) and all(l >= 1 for l in env.length_queue)
+    v.check_flags()
+
+
+def test_eval_batched_vs_farmeval_loop_and_oracle(built_lib):
+    import torch
+    from windgym_b200 import ConstantAgent, FarmEval, V80, VecWindFarmEnv, eval_batched
+    cfg = small_config(2, 2, reward="Baseline", action="wind")
+    wss, wds, tis, t_sim = [9.0, 12.0], [265.0, 275.0], [0.07], 12
+    agent = ConstantAgent([-10, 20, 0, 0])
+    env = VecWindFarmEnv(V80(), 4, config=cfg, eval_mode=True, yaw_init="Defined", device="cuda:0")
+    ds = eval_batched(env, agent, wss, wds, tis, t_sim=t_sim)
+    env.close()
+    assert ds["powerT_a"].shape == (t_sim, 4, 2, 2, 1, 1, 1) and "pct_inc" in ds
+    # yaw moves one degree per step towards the target (SURVEY.md 8a known answer), baseline farm stays greedy
+    assert np.allclose(ds["yaw_a"][5, :, 0, 0, 0, 0, 0], [-5, 5, 0, 0]) and np.allclose(ds["yaw_a"][11, :, 1, 1, 0, 0, 0], [-10, 11, 0, 0])
+    for i, ws in enumerate(wss):
+        for j, wd in enumerate(wds):
+            # --- the reference's serial pattern on the single-env facade: bit-identical (same CUDA path, batch of one)
+            fe = FarmEval(V80(), config=cfg, Baseline_comp=True, yaw_init="Defined", reset_init=False, device="cuda:0")
+            fe.set_wind_vals(ws=ws, ti=0.07, wd=wd)
+            fe.set_yaw_vals(0.0)
+            obs, _ = fe.reset()
+            pw = [fe.fs.windTurbines.power()]
+            pb = [fe.fs_baseline.windTurbines.power()]
+            agent.env = fe
+            for _ in range(1, t_sim):
+                obs, r, _, _, _ = fe.step(agent.predict(obs)[0])
+                pw.append(fe.fs.windTurbines.power()); pb.append(fe.fs_baseline.windTurbines.power())
+            assert fe.fs.time == ds.coords["time0"][i, j, 0, 0] + (t_sim - 1)
+            fe.close()
+            assert np.array_equal(ds["powerT_a"][:, :, i, j, 0, 0, 0], np.array(pw))
+            assert np.array_equal(ds["powerT_b"][:, :, i, j, 0, 0, 0], np.array(pb))
+    # --- one condition against the CPU oracle
+    acts = np.tile(agent.predict()[0].astype(np.float32), (t_sim - 1, 1, 1))
+    ref = oracle_rollout(cfg, np.array([12.0]), np.array([0.07]), np.array([265.0]), np.zeros((1, 4)), acts,
+                         eval_mode=True)
+    rel = np.abs(ds["powerT_a"][1:, :, 1, 0, 0, 0, 0] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
+    assert rel.max() < 1e-4
+    relb = np.abs(ds["powerT_b"][1:, :, 1, 0, 0, 0, 0] - ref["power_base"][0]) / np.maximum(ref["power_base"][0], 1.0)
+    assert relb.max() < 1e-4
+    assert np.allclose(ds["reward"][1:, 1, 0, 0, 0, 0], ref["reward"][0], rtol=2e-4, atol=2e-5)
+
+
+def test_sb3_mlp_policy_rollout_on_device(built_lib):
+    import torch
+    from windgym_b200 import GymVectorEnv, SB3MlpPolicy, V80
+    cfg = small_config(2, 2, reward="Power_avg", action="yaw")
+    env = GymVectorEnv(V80(), 8, config=cfg, device="cuda:0", as_torch=True, seed=0)
+    torch.manual_seed(0)
+    pol = SB3MlpPolicy(env.single_observation_space.shape[0], 4).to("cuda:0")   # PPO_2975000.zip shape: 8 -> 64 -> 64 -> 4
+    obs, _ = env.reset(seed=0)
+    assert obs.is_cuda and obs.shape == (8, 8)
+    tot = 0.0
+    for _ in range(5):
+        act = pol.predict_batch(obs)
+        assert act.is_cuda and act.shape == (8, 4) and float(act.abs().max()) <= 1.0
+        obs, r, term, trunc, infos = env.step(act)
+        assert r.is_cuda and infos["Power agent"].is_cuda
+        tot += float(infos["Power agent"].sum())
+    assert np.isfinite(tot) and tot > 0
+    env.close()

@@ -16,4 +16,13 @@ def __getattr__(name):  # torch-dependent classes are imported lazily so `import
     if name in ("WindFarmEnv", "FarmEval", "WindFarmEnvMulti"):
         from . import envs
         return getattr(envs, name)
+    if name in ("GymVectorEnv", "SB3VecEnv", "RecordEpisodeVals"):
+        from . import vector
+        return getattr(vector, name)
+    if name in ("AgentEval", "eval_batched", "EvalDataset"):
+        from . import evaluate
+        return getattr(evaluate, name)
+    if name in ("BaseAgent", "ConstantAgent", "RandomAgent", "GreedyAgent", "SB3MlpPolicy"):
+        from . import agents
+        return getattr(agents, name)
     raise AttributeError(name)
