@@ -131,6 +131,12 @@ int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream)
 int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float* wd, const float* yaw,
                         const float* power, float* obs, void* cuda_stream);
 
+/* DWMFlowSimulation.get_windspeed(view, include_wakes=True) (render path, Wind_Farm_Env.py:1056; view :470-476):
+ * wake-superposed (u, v, w) of farm `farm` of env `env` at n_points points (x[i], y[i], z) of the wind-aligned
+ * frame of positions_xyz.  x, y: device [n_points]; out_uvw: device [3, n_points]. */
+int wg_flow_field(wg_handle* h, void* state, int32_t env, int32_t farm, const float* x, const float* y,
+                  int32_t n_points, float z, float* out_uvw, void* cuda_stream);
+
 /* Number of kernel launches issued through this handle so far (bench.py "gpu_launches"). */
 int wg_launch_count(const wg_handle* h, uint64_t* out);
 

@@ -391,6 +391,44 @@ class DWMFlowSimulation:
         self.n_step += 1
         self.time += dt
 
-    # render-only API (``Wind_Farm_Env.py:1056``) is out of scope
-    def get_windspeed(self, *a, **k):
-        raise NotImplementedError("flow-field rendering is out of scope (SURVEY.md 8 f-4)")
+    # -- render API (``Wind_Farm_Env.py:1056``) --------------------------------------
+    def wind_at_points(self, x, y, z):
+        """Wake-superposed (u, v, w) at points (x, y, z) of the wind-aligned frame: the superposition rule of
+        ``step`` (bracketing pair of consecutive ages, linear interpolation in x of centre and profile, deficit
+        along the emitting rotor's axis) evaluated at a point instead of over a rotor's quadrature points."""
+        x, y = np.asarray(x, dtype=np.float64).reshape(-1), np.asarray(y, dtype=np.float64).reshape(-1)
+        z = np.broadcast_to(np.asarray(z, dtype=np.float64), x.shape)
+        du, dv = np.zeros(x.size), np.zeros(x.size)
+        for i in range(self.T):
+            if self.count[i] < 2:
+                continue
+            sl = self.slots_by_age(i)
+            xa, ya, za = self.pmut[i, sl, 0], self.pmut[i, sl, 1], self.pmut[i, sl, 2]
+            xp, xn = xa[:-1, None], xa[1:, None]  # younger, older
+            up = (xp <= x[None]) & (x[None] < xn)
+            dn = (xn <= x[None]) & (x[None] < xp)
+            sign = up.astype(np.float64) - dn.astype(np.float64)
+            pi_, ji = np.nonzero(sign)
+            if pi_.size == 0:
+                continue
+            sg_ = sign[pi_, ji]
+            w = (x[ji] - xa[pi_]) / (xa[pi_ + 1] - xa[pi_])
+            yc = ya[pi_] * (1 - w) + ya[pi_ + 1] * w
+            zc = za[pi_] * (1 - w) + za[pi_ + 1] * w
+            rq = np.sqrt(((y[ji] - yc) / self.R) ** 2 + ((z[ji] - zc) / self.R) ** 2)[:, None]
+            for side, wgt in ((0, 1.0 - w), (1, w)):
+                s_ = sl[pi_ + side]
+                Dq = profile_deficit_at(self.prof[i, s_], rq)[:, 0]
+                U0e, _, cg, sg0 = self.pcon[i, s_].T
+                np.add.at(du, ji, sg_ * wgt * U0e * cg * Dq)
+                np.add.at(dv, ji, sg_ * wgt * U0e * sg0 * Dq)
+        return np.stack([self.ws - du, dv, np.zeros(x.size)])
+
+    def get_windspeed(self, view, include_wakes=True, xarray=False):
+        """``[3, len(view.x), len(view.y)]`` on an XYView-like object (attributes x, y, z)."""
+        gx, gy = np.meshgrid(np.asarray(view.x, dtype=np.float64), np.asarray(view.y, dtype=np.float64), indexing="ij")
+        if not include_wakes:
+            out = np.zeros((3,) + gx.shape)
+            out[0] = self.ws
+            return out
+        return self.wind_at_points(gx, gy, float(np.asarray(view.z).reshape(-1)[0])).reshape((3,) + gx.shape)

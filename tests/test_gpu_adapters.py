@@ -102,3 +102,47 @@ def test_sb3_mlp_policy_rollout_on_device(built_lib):
         tot += float(infos["Power agent"].sum())
     assert np.isfinite(tot) and tot > 0
     env.close()
+
+
+def test_flow_field_and_render_vs_oracle(built_lib):
+    """f-4: fs.get_windspeed on an XY view (the render path) against the oracle's superposition at points."""
+    from oracle import dwm_numpy as dwm
+    from oracle.v80 import V80 as OV80
+    from windgym_b200 import FarmEval, V80
+    from windgym_b200.config import grid_layout
+    from windgym_b200.envs import XYView
+    cfg = small_config(2, 2, reward="Power_avg", action="wind")
+    ws, wd = 9.0, 268.0
+    env = FarmEval(V80(), config=cfg, yaw_init="Defined", reset_init=False, render_mode="rgb_array", device="cuda:0")
+    env.set_wind_vals(ws=ws, ti=0.07, wd=wd)
+    env.set_yaw_vals([20.0, -15.0, 0.0, 10.0])
+    env.reset()
+    n_spin, _, _ = env.vec.ec.reset_integers(np.array([ws]), np.array([wd]))
+    n_flow = int(n_spin[0]) + env.steps_on_reset
+    assert env.fs.time == n_flow
+    # oracle flow in the same state
+    x, y = grid_layout(80.0, 4, 4, 2, 2)
+    wt = dwm.PyWakeWindTurbines(x, y, OV80())
+    fs = dwm.DWMFlowSimulation(dwm.TurbulenceFieldSite(ws, dwm.RandomTurbulence(0, ws)), wt, wind_direction=wd, dt=1,
+                               d_particle=0.2)
+    wt.yaw = [20.0, -15.0, 0.0, 10.0]
+    for _ in range(n_flow):
+        fs.step()
+    xt, yt = env.fs.windTurbines.positions_xyz[:2]
+    view = XYView(x=np.linspace(xt.min() - 150, xt.max() + 700, 61), y=np.linspace(yt.min() - 150, yt.max() + 150, 47), z=70.0)
+    got = env.fs.get_windspeed(view, include_wakes=True, xarray=False)
+    ref = fs.get_windspeed(view)
+    assert got.shape == ref.shape == (3, 61, 47)
+    assert ref[0].min() < 0.75 * ws and ref[0].max() <= ws + 1e-9      # there are wakes in the view
+    assert np.abs(got[0] - ref[0]).max() < 2e-4 * ws, np.abs(got[0] - ref[0]).max()
+    assert np.abs(got[1] - ref[1]).max() < 2e-4 * ws
+    assert np.abs(got[1]).max() > 0.05                                 # yawed rotors deflect: lateral component
+    free = env.fs.get_windspeed(view, include_wakes=False)
+    assert np.all(free[0] == ws) and np.all(free[1:] == 0)
+    fa = env.fs.get_windspeed(view, xarray=True)
+    assert np.array_equal(fa[0], got[0]) and np.array_equal(fa.x.values, view.x)
+    # render: RGB frame of the reference's 250 x 250 view
+    img = env.render()
+    assert img.shape == (250, 250, 3) and img.dtype == np.uint8 and len(np.unique(img.reshape(-1, 3), axis=0)) > 20
+    assert (img.reshape(-1, 3).sum(1) == 0).sum() >= 4 * 20               # rotors drawn
+    env.close()

@@ -64,6 +64,8 @@ SYMBOLS = {
     "wg_flow_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_mes_push_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "wg_flow_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                C.c_float, C.c_void_p, C.c_void_p]),
     "wg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),
     "wg_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "wg_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),

@@ -429,6 +429,19 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   return WG_OK;
 }
 
+int wg_flow_field(wg_handle* h, void* state, int32_t env, int32_t farm, const float* x, const float* y,
+                  int32_t n_points, float z, float* out_uvw, void* cuda_stream) {
+  if (!h || !state || !x || !y || !out_uvw) return fail(WG_ERR_INVALID, "wg_flow_field: null argument");
+  if (env < 0 || env >= h->cfg.n_envs || farm < 0 || farm >= h->cfg.n_farms)
+    return fail(WG_ERR_INVALID, "wg_flow_field: env / farm index out of range");
+  if (n_points < 0) return fail(WG_ERR_INVALID, "n_points must be >= 0");
+  if (n_points == 0) return WG_OK;
+  wg::Dev d = bind(h, state);
+  WG_LAUNCH(wg::launch_flow_field(d, env, farm, x, y, n_points, z, out_uvw, (cudaStream_t)cuda_stream),
+            "wg_flow_field_kernel");
+  return WG_OK;
+}
+
 int wg_profile_enable(wg_handle* h, int32_t on) {
   if (!h) return fail(WG_ERR_INVALID, "wg_profile_enable: null argument");
   h->profiling = on != 0;

@@ -1,0 +1,77 @@
+// wg_flow_field_kernel -- DWMFlowSimulation.get_windspeed(view, include_wakes=True) on a set of points of one
+// env's farm (render path, reference call site WindGym/Wind_Farm_Env.py:1056; view built at :470-476 as a
+// 250 x 250 XYView at hub height).  Second consumer of the superposition rule of the flow kernel: for every
+// point, every chain is scanned pair by pair (consecutive ages); a pair that brackets the point's x contributes
+// the two stations' deficits, interpolated linearly in x, evaluated at the point's distance from the interpolated
+// wake centre (oracle/dwm_numpy.py:wind_at_points).  One thread per point; the pair scan reads the same station
+// in every lane (broadcast loads), the profile rows come through L2.
+#include "wg_internal.cuh"
+
+namespace wg {
+
+__device__ __forceinline__ float row_deficit(const float* __restrict__ row, int key, float s) {
+  if (s >= (float)(WG_NR - 1)) return 0.f;
+  const int j0 = min((int)s, WG_NR - 2), j1 = j0 + 1;
+  const float fr = s - (float)j0;
+  const float u0 = row[(((j0 >> 2) ^ key) << 2) | (j0 & 3)];
+  const float u1 = (j1 == WG_NR - 1) ? 1.f : row[(((j1 >> 2) ^ key) << 2) | (j1 & 3)];
+  return (1.f - u0) * (1.f - fr) + (1.f - u1) * fr;
+}
+
+__global__ void __launch_bounds__(128) wg_flow_field_kernel(const Dev d, int b, int f, const float* __restrict__ px,
+                                                            const float* __restrict__ py, int n, float z,
+                                                            float* __restrict__ out) {
+  const int T = d.T, P = d.P;
+  const int bf = b * d.F + f;
+  const float ws = d.ws[b], rR = 1.f / d.R;
+  const int par = d.n_step[bf] & 1;
+  const float* __restrict__ prof = d.prof + (size_t)bf * T * P * WG_NR;
+  const float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;
+  const float* __restrict__ pm = d.pmut + ((size_t)par * d.B * d.F + bf) * T * P * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = px[i], y = py[i];
+    float du = 0.f, dv = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int cnt = d.count[bf * T + t], head = d.head[bf * T + t];
+      if (cnt < 2) continue;
+      // ages: a = 0 youngest (slot head-1) ... cnt-1 oldest
+      int s0 = head - 1;
+      if (s0 < 0) s0 += P;
+      float4 p0 = *reinterpret_cast<const float4*>(pm + ((size_t)t * P + s0) * 4);
+      for (int a = 1; a < cnt; ++a) {
+        int s1 = s0 - 1;
+        if (s1 < 0) s1 += P;
+        const float4 p1 = *reinterpret_cast<const float4*>(pm + ((size_t)t * P + s1) * 4);
+        // younger p0, older p1: up = x0 <= x < x1 (+1), dn = x1 <= x < x0 (-1)
+        const bool up = p0.x <= x && x < p1.x, dn = p1.x <= x && x < p0.x;
+        if (up || dn) {
+          const float sgn = up ? 1.f : -1.f;
+          const float w = (x - p0.x) / (p1.x - p0.x);
+          const float yc = p0.y * (1.f - w) + p1.y * w, zc = p0.z * (1.f - w) + p1.z * w;
+          const float ry = (y - yc) * rR, rz = (z - zc) * rR;
+          const float s = sqrtf(ry * ry + rz * rz) * (1.f / DR);
+          const float4 c0 = *reinterpret_cast<const float4*>(pcon + ((size_t)t * P + s0) * 4);
+          const float4 c1 = *reinterpret_cast<const float4*>(pcon + ((size_t)t * P + s1) * 4);
+          const float D0 = row_deficit(prof + ((size_t)t * P + s0) * WG_NR, s0 & 7, s);
+          const float D1 = row_deficit(prof + ((size_t)t * P + s1) * WG_NR, s1 & 7, s);
+          du += sgn * ((1.f - w) * c0.x * c0.z * D0 + w * c1.x * c1.z * D1);
+          dv += sgn * ((1.f - w) * c0.x * c0.w * D0 + w * c1.x * c1.w * D1);
+        }
+        s0 = s1;
+        p0 = p1;
+      }
+    }
+    out[i] = ws - du;
+    out[n + i] = dv;
+    out[2 * n + i] = 0.f;
+  }
+}
+
+cudaError_t launch_flow_field(const Dev& d, int b, int f, const float* px, const float* py, int n, float z, float* out,
+                              cudaStream_t s) {
+  const int grid = min((n + 127) / 128, 148 * 8);
+  wg_flow_field_kernel<<<grid, 128, 0, s>>>(d, b, f, px, py, n, z, out);
+  return cudaGetLastError();
+}
+
+}  // namespace wg

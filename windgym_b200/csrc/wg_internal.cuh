@@ -105,5 +105,7 @@ void set_rotor_points(const float* qy, const float* qz);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
+cudaError_t launch_flow_field(const Dev& d, int b, int f, const float* px, const float* py, int n, float z, float* out,
+                              cudaStream_t s);
 
 }  // namespace wg

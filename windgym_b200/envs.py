@@ -207,6 +207,50 @@ class _FlowView:
     def run(self, t):
         self.v.flow_steps(int(round(t / self.v.ec.dt_sim)))
 
+    def get_windspeed(self, view, include_wakes=True, xarray=False):
+        """dynamiks ``get_windspeed`` for an ``XYView``-like object (attributes ``x``, ``y``, ``z``): array
+        [3, len(x), len(y)] of (u, v, w).  ``xarray=True`` returns a ``FieldArray`` with the ``.x/.y.values`` and
+        ``[component]`` access ``_render_frame`` uses (Wind_Farm_Env.py:1056-1063)."""
+        x, y = np.asarray(view.x, dtype=np.float64), np.asarray(view.y, dtype=np.float64)
+        z = float(np.asarray(getattr(view, "z", self.v.ec.hub_height)).reshape(-1)[0])
+        if include_wakes:
+            uvw = self.v.flow_field(x, y, z, env=self.b, farm=self.f).cpu().numpy().astype(np.float64)
+        else:
+            uvw = np.zeros((3, x.size, y.size))
+            uvw[0] = float(self.v.ws[self.b])
+        return FieldArray(uvw, x, y) if xarray else uvw
+
+
+class XYView:
+    """``dynamiks.views.XYView`` stand-in: a horizontal plane ``x`` x ``y`` at height ``z`` (wind-aligned frame)."""
+
+    def __init__(self, x, y, z, ax=None, adaptive=False):
+        self.x, self.y, self.z, self.ax, self.adaptive = np.asarray(x), np.asarray(y), z, ax, adaptive
+
+
+class _Coord:
+    def __init__(self, values):
+        self.values = values
+
+
+class FieldArray:
+    """What ``get_windspeed(..., xarray=True)`` returns without xarray: ``uvw[0]`` is the u field [x, y]."""
+
+    def __init__(self, values, x, y):
+        self.values, self.x, self.y = values, _Coord(x), _Coord(y)
+
+    def __getitem__(self, i):
+        return self.values[i]
+
+
+def _viridis(t):
+    """Tiny viridis-like colour map (5 knots, linear): t in [0, 1] -> uint8 RGB."""
+    knots = np.array([[68, 1, 84], [59, 82, 139], [33, 145, 140], [94, 201, 98], [253, 231, 37]], dtype=np.float64)
+    t = np.clip(t, 0.0, 1.0) * (len(knots) - 1)
+    i = np.minimum(t.astype(int), len(knots) - 2)
+    f = (t - i)[..., None]
+    return (knots[i] * (1 - f) + knots[i + 1] * f).astype(np.uint8)
+
 
 class WindFarmEnv(_GymEnv):
     """Drop-in for ``WindGym.WindFarmEnv`` (Wind_Farm_Env.py:47-70): one env, numpy in / numpy out."""
@@ -221,8 +265,6 @@ class WindFarmEnv(_GymEnv):
                  device="cuda:0"):
         if HTC_path is not None:
             raise NotImplementedError("HAWC2 turbines (HTC_path) are out of scope: external aero-elastic co-simulation")
-        if sample_site is not None:
-            raise NotImplementedError("site-based wind sampling is the f-4 row of SURVEY.md section 8 (not built yet)")
         if render_mode is not None and render_mode not in self.metadata["render_modes"]:
             raise ValueError(f"render_mode must be one of {self.metadata['render_modes']}")
         self.render_mode = render_mode
@@ -230,7 +272,8 @@ class WindFarmEnv(_GymEnv):
                                   TI_min_mes=TI_min_mes, TI_max_mes=TI_max_mes, TurbBox=TurbBox, turbtype=turbtype,
                                   Baseline_comp=Baseline_comp, yaw_init=yaw_init, seed=seed, dt_sim=dt_sim,
                                   dt_env=dt_env, yaw_step=yaw_step, fill_window=fill_window, device=device,
-                                  multi_agent=self._multi_agent, eval_mode=self._eval_mode)
+                                  multi_agent=self._multi_agent, eval_mode=self._eval_mode, sample_site=sample_site)
+        self.sample_site = sample_site
         v, ec = self.vec, self.vec.ec
         self.turbine, self.seed = turbine, seed
         self.n_turb, self.x_pos, self.y_pos = ec.n_turb, ec.x_pos, ec.y_pos
@@ -328,8 +371,38 @@ class WindFarmEnv(_GymEnv):
         self.timestep += 1
         return self._obs_numpy(obs), float(rew[0]), False, bool(trunc[0]), self._get_info()
 
+    def init_render(self):
+        """Wind_Farm_Env.py:464-478: a 250 x 250 hub-height view around the (rotated) farm."""
+        x_turb, y_turb = self.fs.windTurbines.positions_xyz[:2]
+        self.a = np.linspace(-200 + min(x_turb), 1000 + max(x_turb), 250)
+        self.b = np.linspace(-200 + min(y_turb), 200 + max(y_turb), 250)
+        self.view = XYView(z=self.turbine.hub_height(), x=self.a, y=self.b, adaptive=False)
+
     def render(self):
-        raise NotImplementedError("flow-field rendering is the f-4 row of SURVEY.md section 8 (not built yet)")
+        if self.render_mode == "rgb_array":
+            return self._render_frame()
+
+    def _render_frame(self, baseline=False):
+        """Wind_Farm_Env.py:1040-1083 without matplotlib: the u field of the hub-height view as an RGB image
+        [len(y), len(x), 3] uint8 (row 0 = smallest y), rotors drawn as black segments across their yawed planes."""
+        fs_use = self.fs_baseline if baseline else self.fs
+        self.init_render()
+        uvw = fs_use.get_windspeed(self.view, include_wakes=True, xarray=True)
+        u = uvw[0].T                                              # [y, x] like pcolormesh(x, y, u.T)
+        img = _viridis((u - 0.3 * self.ws) / (0.8 * self.ws))
+        wt = fs_use.windTurbines
+        xt, yt = wt.positions_xyz[:2]
+        R = 0.5 * self.turbine.diameter()
+        for x0, y0, g in zip(xt, yt, np.deg2rad(wt.yaw)):
+            for s in np.linspace(-R, R, 41):                      # rotor plane: normal turned by the yaw offset
+                xi = np.searchsorted(self.a, x0 + s * np.sin(g))
+                yi = np.searchsorted(self.b, y0 + s * np.cos(g))
+                if 0 <= xi < self.a.size and 0 <= yi < self.b.size:
+                    img[yi, xi] = 0
+        return img
+
+    def plot_frame(self, baseline=False):
+        return self._render_frame(baseline=baseline)
 
     def close(self):
         self.vec.close()

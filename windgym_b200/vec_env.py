@@ -24,7 +24,7 @@ class VecWindFarmEnv:
     def __init__(self, turbine, n_envs, yaml_path=None, config=None, n_passthrough=5, TI_min_mes=0.0,
                  TI_max_mes=0.50, TurbBox="Default", turbtype="None", Baseline_comp=False, yaw_init=None,
                  seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True, device="cuda:0",
-                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False):
+                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None):
         cfg = config if config is not None else load_yaml(yaml_path)
         self.ec = ec = EnvConfig(cfg, turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes,
                                  TI_max_mes=TI_max_mes, turbtype=turbtype, Baseline_comp=Baseline_comp,
@@ -37,6 +37,8 @@ class VecWindFarmEnv:
         if self.device.type != "cuda":
             raise _lib.WgError("VecWindFarmEnv runs on a CUDA device only (no CPU fallback)")
         self.seed = seed
+        self.sample_site = sample_site
+        self._site_tables = None
         self.x_pos, self.y_pos = ec.x_pos, ec.y_pos
         self.yaw_min, self.yaw_max, self.yaw_step = ec.yaw_min, ec.yaw_max, yaw_step
         self.Baseline_comp = ec.Baseline_comp
@@ -173,9 +175,17 @@ class VecWindFarmEnv:
                 rng = np.random.default_rng(seed)
             else:
                 rng = np.random.default_rng([seed, i, self._episode])
-            ws[i] = rng.uniform(low=ec.ws_min, high=ec.ws_max)
-            ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
-            wd[i] = rng.uniform(low=ec.wd_min, high=ec.wd_max)
+            if self.sample_site is None:
+                ws[i] = rng.uniform(low=ec.ws_min, high=ec.ws_max)
+                ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
+                wd[i] = rng.uniform(low=ec.wd_min, high=ec.wd_max)
+            else:  # site-based sampling, Wind_Farm_Env.py:569-596 (sector frequency -> Weibull A, k -> clip)
+                dirs, As, ks, freqs = self._site()
+                idx = rng.choice(np.arange(dirs.size), 1, p=freqs)
+                wd_s, ws_s = dirs[idx].item(), (As[idx] * rng.weibull(ks[idx])).item()
+                wd[i] = np.clip(wd_s, ec.wd_min, ec.wd_max)
+                ws[i] = np.clip(ws_s, ec.ws_min, ec.ws_max)
+                ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
             if ec.yaw_init_mode == "Random":
                 yaw0[i] = rng.uniform(low=-ec.yaw_start, high=ec.yaw_start, size=T)
         for k, arr in (("ws", ws), ("ti", ti), ("wd", wd)):
@@ -188,6 +198,18 @@ class VecWindFarmEnv:
                                  "are not the right length.")
             yaw0[list(envs)] = yv if yv.size == T else np.ones(T) * yv.reshape(-1)[0]
         return ws, ti, wd, yaw0
+
+    def _site(self):
+        """Wind resource tables of ``sample_site`` (py_wake site protocol: ``local_wind(x, y, wd, ws)`` with
+        ``Sector_frequency_ilk``, ``Weibull_A_ilk``, ``Weibull_k_ilk``), read once (Wind_Farm_Env.py:571-577).
+        The reference draws from the GLOBAL numpy RNG here; this class uses the env's seeded stream."""
+        if self._site_tables is None:
+            dirs = np.arange(0, 360, 1)
+            lw = self.sample_site.local_wind(x=0, y=0, wd=dirs, ws=np.arange(3, 25, 1))
+            freqs = np.asarray(lw.Sector_frequency_ilk)[0, :, 0].astype(np.float64)
+            self._site_tables = (dirs, np.asarray(lw.Weibull_A_ilk)[0, :, 0].astype(np.float64),
+                                 np.asarray(lw.Weibull_k_ilk)[0, :, 0].astype(np.float64), freqs / freqs.sum())
+        return self._site_tables
 
     def reset(self, seed=None, mask=None, wind=None, yaw0=None):
         """WindFarmEnv.reset for the masked envs (all when ``mask`` is None).
@@ -238,6 +260,21 @@ class VecWindFarmEnv:
     def flow_steps(self, n):
         """DWMFlowSimulation.run(n*dt) for every env and farm, without measurement bookkeeping."""
         _lib.check(self.lib.wg_flow_steps(self._h, _ptr(self._state), int(n), self._stream()))
+
+    def flow_field(self, x, y, z=None, env=0, farm=0):
+        """``fs.get_windspeed(XYView(x, y, z), include_wakes=True)`` of one env's farm (render path,
+        Wind_Farm_Env.py:470-476, :1056): wake-superposed (u, v, w) on the grid x[i] x y[j] at height z
+        (default: hub height), wind-aligned frame.  Returns a device tensor [3, len(x), len(y)]."""
+        xs = torch.as_tensor(np.asarray(x, dtype=np.float32), device=self.device)
+        ys = torch.as_tensor(np.asarray(y, dtype=np.float32), device=self.device)
+        gx, gy = torch.meshgrid(xs, ys, indexing="ij")
+        px, py = gx.reshape(-1).contiguous(), gy.reshape(-1).contiguous()
+        out = torch.empty((3, px.numel()), dtype=torch.float32, device=self.device)
+        zz = float(self.ec.hub_height if z is None else z)
+        _lib.check(self.lib.wg_flow_field(self._h, _ptr(self._state), int(env), int(farm), _ptr(px), _ptr(py),
+                                          int(px.numel()), zz, _ptr(out), self._stream()))
+        self._keep_field = (px, py)
+        return out.reshape(3, xs.numel(), ys.numel())
 
     def mes_push_extract(self, ws, wd, yaw, power):
         """farm_mes.add_measurements + get_measurements(scaled=True) + clip on [B,T] device tensors."""
