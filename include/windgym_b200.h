@@ -92,6 +92,8 @@ typedef struct {
   const int32_t* k_emit;     /* [B] particle release cadence in flow steps              */
   const int32_t* t_developed;/* [B] int(2*dist/ws)/dt spin-up flow steps (:729,:734)    */
   const int32_t* time_max;   /* [B] int(t_inflow*n_passthrough) (:732); 9999999 for FarmEval */
+  const float* tb_offset;    /* [B,3] env position inside the shared turbulence box [m]; NULL without a box */
+  const float* tb_scale;     /* [B] scale_TI(TI, U) factor TI*U/std(u_box) (:617,:638,:657); NULL without a box */
 } wg_reset_args;
 
 typedef struct wg_handle wg_handle;
@@ -130,6 +132,14 @@ int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream)
  * Wind_Farm_Env.py:513-520) on the state's ring buffers.  ws/wd/yaw/power: device [B,T]. */
 int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float* wd, const float* yaw,
                         const float* power, float* obs, void* cuda_stream);
+
+/* TurbulenceFieldSite over a MannTurbulenceField (_def_site, Wind_Farm_Env.py:598-678): attach one periodic
+ * turbulence box, shared read-only by every env of the handle, in the two layouts the flow kernel samples:
+ * raw_uvw0 device [nx,ny,nz,4] f32 (u, v, w, 0) and lp_vw device [nx,ny,nz,2] f32 ((v, w) low-pass filtered in
+ * y, z -- the scales that meander the wake centres).  Caller-owned, must outlive the handle's launches.
+ * Both NULL: back to uniform inflow (turbtype "None").  Takes effect at the next wg_reset. */
+int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, int32_t nx, int32_t ny, int32_t nz,
+                      float dx, float dy, float dz);
 
 /* DWMFlowSimulation.get_windspeed(view, include_wakes=True) (render path, Wind_Farm_Env.py:1056; view :470-476):
  * wake-superposed (u, v, w) of farm `farm` of env `env` at n_points points (x[i], y[i], z) of the wind-aligned

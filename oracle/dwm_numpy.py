@@ -14,7 +14,10 @@ inflow U0e):
 * Frame: wind aligned, theta = 270deg - wd; x' = dx cos(theta) + dy sin(theta), y' = -dx sin(theta) + dy cos(theta)
   about the layout centroid (matches the positions printed in the reference notebook).
 * Ambient: uniform (ws, 0, 0) (``TurbulenceFieldSite`` over ``RandomTurbulence(ti=0)`` -- the deterministic
-  ``turbtype="None"`` path, ``Wind_Farm_Env.py:661-665``).
+  ``turbtype="None"`` path, ``Wind_Farm_Env.py:661-665``), or (ws, 0, 0) + a frozen Mann box advected with ws
+  (``oracle/mann_numpy.py``; ``MannLoad`` / ``MannGenerate`` / ``MannFixed``, ``Wind_Farm_Env.py:612-659``): the
+  low-pass filtered (v', w') at a particle's centre move it (meandering, Larsen et al. 2008), the raw box averaged
+  over the rotor's quadrature points is added to the rotor inflow.  Added wake turbulence is not restated.
 * Turbine: tabular P/CT, py_wake ``SimpleYawModel``: P = P_tab(u cos g), CT = CT_tab(u cos g) cos^2 g,
   induction a = (1 - sqrt(1 - CT)) / 2.
 * Wake particles (Larsen et al. 2008, Wind Energy 11:377): one chain per turbine; a particle is released at
@@ -297,6 +300,8 @@ class DWMFlowSimulation:
         self.rotor_avg_windspeed = np.tile(np.array([self.ws, 0.0, 0.0]), (T, 1))
         self.qpts = rotor_points()
         self.last_nu = None
+        tf = getattr(site, "turbulenceField", None)
+        self.tf = tf if hasattr(tf, "sample") else None  # Mann box (oracle/mann_numpy.py); None = uniform inflow
 
     # -- helpers --------------------------------------------------------------------------------
     def slots_by_age(self, t):
@@ -333,12 +338,17 @@ class DWMFlowSimulation:
             duc = 1.0 - uc
             vx = self.ws - K_HILL * duc * U0e * cg
             vy = K_HILL * duc * U0e * sg
+            vz = np.zeros_like(vy)
+            if self.tf is not None:  # meandering: the large-scale lateral / vertical fluctuations carry the wake centre
+                vl, wl = self.tf.sample_lp(x, y, z, self.time, self.ws)
+                vy = vy + vl
+                vz = wl
             dx = vx * dt
             xt_mid = (x + 0.5 * dx - self.xr[ti]) / R
             Un, nu = ainslie_march(U, dx / R, xt_mid, knu1)
             self.last_nu = nu
             self.prof[ti, si] = Un
-            self.pmut[ti, si] = np.stack([x + dx, y + vy * dt, z, Un[:, 0]], axis=1)
+            self.pmut[ti, si] = np.stack([x + dx, y + vy * dt, z + vz * dt, Un[:, 0]], axis=1)
         # 3. rotor inflow: ambient minus superposed upstream deficits
         du = np.zeros(T)
         dv = np.zeros(T)
@@ -370,7 +380,13 @@ class DWMFlowSimulation:
                 U0e, _, cg, sg0 = self.pcon[i, s_].T
                 np.add.at(du, ji, sg_ * wgt * U0e * cg * Dq)
                 np.add.at(dv, ji, sg_ * wgt * U0e * sg0 * Dq)
-        self.rotor_avg_windspeed = np.stack([self.ws - du, dv, np.zeros(T)], axis=1)
+        amb = np.zeros((3, T))
+        if self.tf is not None:  # rotor-averaged ambient fluctuation at the new time level
+            py = self.yr[:, None] + self.qpts[None, :, 0] * R
+            pz = self.zh + self.qpts[None, :, 1] * R
+            px = np.broadcast_to(self.xr[:, None], py.shape)
+            amb = self.tf.sample(px, py, pz, self.time + dt, self.ws).mean(axis=2)
+        self.rotor_avg_windspeed = np.stack([self.ws + amb[0] - du, amb[1] + dv, amb[2]], axis=1)
         # 4./5. turbine update and particle release
         if self.n_step % self.k_emit == 0:
             u = self.rotor_avg_windspeed[:, 0]
@@ -422,7 +438,8 @@ class DWMFlowSimulation:
                 U0e, _, cg, sg0 = self.pcon[i, s_].T
                 np.add.at(du, ji, sg_ * wgt * U0e * cg * Dq)
                 np.add.at(dv, ji, sg_ * wgt * U0e * sg0 * Dq)
-        return np.stack([self.ws - du, dv, np.zeros(x.size)])
+        amb = self.tf.sample(x, y, z, self.time, self.ws) if self.tf is not None else np.zeros((3, x.size))
+        return np.stack([self.ws + amb[0] - du, amb[1] + dv, amb[2]])
 
     def get_windspeed(self, view, include_wakes=True, xarray=False):
         """``[3, len(view.x), len(view.y)]`` on an XYView-like object (attributes x, y, z)."""

@@ -212,9 +212,14 @@ class WindFarmEnvOracle:
 
     def __init__(self, turbine, cfg, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.5, turbtype="None",
                  Baseline_comp=False, yaw_init=None, seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True,
-                 eval_mode=False, reset_init=True, noise_seed=0):
-        if turbtype != "None":
-            raise NotImplementedError("only the deterministic turbtype='None' site is restated")
+                 eval_mode=False, reset_init=True, noise_seed=0, turb_field=None):
+        if turbtype not in ("None", "MannFixed", "MannGenerate", "MannLoad"):
+            raise NotImplementedError("turbtype 'Random' (white-noise field) is not restated")
+        self.turbtype = turbtype
+        self.turb_field = turb_field      # oracle.mann_numpy.MannTurbulenceField for the Mann site types
+        self.turb_offset = (0.0, 0.0, 0.0)
+        if turbtype != "None" and turb_field is None:
+            raise ValueError("a Mann turbtype needs turb_field (the box the device path was given)")
         self.turbine, self.cfg = turbine, cfg
         self.n_passthrough, self.dt, self.dt_env, self.yaw_step = n_passthrough, dt_sim, dt_env, yaw_step
         if dt_env % dt_sim != 0:
@@ -296,7 +301,13 @@ class WindFarmEnvOracle:
 
     def _new_fs(self):
         wts = dwm.PyWakeWindTurbines(self.x_pos, self.y_pos, self.turbine)
-        site = dwm.TurbulenceFieldSite(ws=self.ws, turbulenceField=dwm.RandomTurbulence(ti=0, ws=self.ws))
+        if self.turbtype == "None":  # Wind_Farm_Env.py:661-665
+            tf = dwm.RandomTurbulence(ti=0, ws=self.ws)
+        else:                        # :612-659: the box is scaled to the episode's TI and wind speed
+            tf = self.turb_field
+            tf.offset = np.asarray(self.turb_offset, dtype=np.float64)
+            tf.scale_TI(TI=self.ti, U=self.ws)
+        site = dwm.TurbulenceFieldSite(ws=self.ws, turbulenceField=tf)
         return dwm.DWMFlowSimulation(site, wts, wind_direction=self.wd, dt=self.dt, d_particle=self.d_particle)
 
     def _measure(self):
@@ -309,8 +320,11 @@ class WindFarmEnvOracle:
     def _obs(self):
         return np.clip(self.mes.get(True), -1.0, 1.0).astype(np.float32)
 
-    def reset(self, seed=None, wind=None, yaw0=None):
-        """Wind_Farm_Env.py:680-802.  ``wind=(ws, ti, wd)`` / ``yaw0`` bypass the RNG draws."""
+    def reset(self, seed=None, wind=None, yaw0=None, turb_offset=None):
+        """Wind_Farm_Env.py:680-802.  ``wind=(ws, ti, wd)`` / ``yaw0`` bypass the RNG draws; ``turb_offset`` is the
+        env's position inside the shared turbulence box (Mann site types)."""
+        if turb_offset is not None:
+            self.turb_offset = turb_offset
         if seed is not None:
             self.np_random = np.random.default_rng(seed)
         self.timestep = 0

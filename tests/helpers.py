@@ -57,14 +57,14 @@ def rich_config(nx=2, ny=2, **over):
     return c
 
 
-def oracle_rollout(cfg, ws, ti, wd, yaw0, acts, multi=False, **kw):
+def oracle_rollout(cfg, ws, ti, wd, yaw0, acts, multi=False, reset_kw=None, **kw):
     """Run the CPU oracle env for every batch entry.  acts: [steps, B, T].  Returns per-env stacked arrays."""
     B = len(ws)
     out = {k: [] for k in ("obs0", "obs", "reward", "power", "yaw", "ws_turb", "trunc", "power_base", "yaw_base",
                            "time_max", "t_developed")}
     for b in range(B):
         env = WindFarmEnvOracle(OracleV80(), cfg, reset_init=False, **kw)
-        o0, _ = env.reset(wind=(ws[b], ti[b], wd[b]), yaw0=yaw0[b])
+        o0, _ = env.reset(wind=(ws[b], ti[b], wd[b]), yaw0=yaw0[b], **(reset_kw or {}))
         rec = {k: [] for k in ("obs", "reward", "power", "yaw", "ws_turb", "trunc", "power_base", "yaw_base")}
         if multi:
             o0 = np.stack(env.mes.get_multi())

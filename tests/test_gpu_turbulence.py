@@ -1,0 +1,92 @@
+"""GPU: ambient Mann turbulence -- device generator vs oracle, and the flow kernel with a box
+(meandering wake centres + rotor-plane fluctuations) against the fp64 oracle on the same box, offsets and TI."""
+import numpy as np
+import pytest
+
+from oracle import mann_numpy as mn
+from tests.helpers import oracle_rollout, small_config
+
+pytestmark = pytest.mark.gpu
+
+N, D3 = (256, 64, 32), (4.0, 6.0, 6.0)     # 1024 m x 384 m x 192 m periodic box
+
+
+def _boxes(lowpass=160.0):
+    import torch
+    from windgym_b200.mann import MannBox
+    noise = mn.box_noise(N, 11)
+    ref = mn.mann_box(0.1, 33.6, 3.9, N, D3, noise=noise)
+    box = MannBox.generate(0.1, 33.6, 3.9, N, D3, device="cuda:0", noise=noise, lowpass_width=lowpass)
+    return ref, box
+
+
+def test_device_generator_matches_oracle(built_lib):
+    ref, box = _boxes()
+    got = box.raw[..., :3].permute(3, 0, 1, 2).cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-5 * ref.std()
+    f = mn.MannTurbulenceField(ref, D3, lowpass_width=160.0)
+    assert np.abs(box.lp.permute(3, 0, 1, 2).cpu().numpy() - f.uvw_lp[1:]).max() < 2e-5 * ref.std()
+    # production path: seeded device noise, complex64 transform for big boxes -- statistics only
+    from windgym_b200.mann import MannBox
+    big = MannBox.generate(Nxyz=(512, 128, 64), dxyz=(3.0, 3.0, 3.0), seed=1234, device="cuda:0")
+    u = big.raw[..., 0]
+    assert abs(float(u.mean())) < 1e-3 and 0.5 < big.std_u < 3.0
+    assert float(big.raw[..., 0].std()) > float(big.raw[..., 1].std()) > float(big.raw[..., 2].std())
+
+
+@pytest.mark.parametrize("reward", ["Power_avg", "Baseline"])
+def test_flow_with_turbulence_box_vs_oracle(built_lib, reward):
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    ref_box, box = _boxes()
+    cfg = small_config(2, 2, reward=reward, action="wind")
+    B, T, steps = 3, 4, 6
+    rng = np.random.default_rng(3)
+    ws, ti, wd = rng.uniform(8, 13, B), rng.uniform(0.05, 0.12, B), rng.uniform(262, 278, B)
+    yaw0 = rng.uniform(-15, 15, (B, T))
+    off = rng.uniform(0, 1, (B, 3)) * (np.array(N) * np.array(D3))
+    acts = rng.uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="MannFixed", turb_box=box)
+    obs0 = env.reset(wind=(ws, ti, wd), yaw0=yaw0, turb_offset=off)[0].cpu().numpy().copy()
+    pw, yw, ob, rw, uvw = [], [], [], [], []
+    for a in acts:
+        o, r, _, _, info = env.step(torch.as_tensor(a))
+        pw.append(info["Power pr turbine agent"].cpu().numpy().copy()); ob.append(o.cpu().numpy().copy())
+        rw.append(r.cpu().numpy().copy())
+        uvw.append(torch.stack([env.state[k][:, 0] for k in ("u", "v", "w")], -1).cpu().numpy().copy())
+    env.check_flags()
+    pw, ob, rw, uvw = np.array(pw), np.array(ob), np.array(rw), np.array(uvw)
+    z = env.state["pmut"][:, :, 0].cpu().numpy()[..., 2]
+    assert np.abs(uvw[..., 2]).max() > 1e-3 and np.abs(z[z != 0] - 70.0).max() > 0.05   # w' at rotors, wakes meander in z
+    for b in range(B):
+        field = mn.MannTurbulenceField(ref_box, D3, lowpass_width=160.0)
+        ref = oracle_rollout(cfg, ws[b:b + 1], ti[b:b + 1], wd[b:b + 1], yaw0[b:b + 1], acts[:, b:b + 1],
+                             turbtype="MannFixed", turb_field=field, reset_kw=dict(turb_offset=off[b]))
+        rel = np.abs(pw[:, b] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
+        assert rel.max() < 1e-4, f"env {b}: power rel err {rel.max():.3e}"
+        assert np.allclose(obs0[b], ref["obs0"][0], atol=2e-5)
+        assert np.allclose(ob[:, b], ref["obs"][0], atol=2e-5)
+        assert np.allclose(rw[:, b], ref["reward"][0], rtol=2e-4, atol=2e-5)
+    # turbulence makes the rotor inflow fluctuate: the same farm without a box sees a steady free-stream front row
+    env0 = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0")
+    env0.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    up = env.state["xr"].cpu().numpy().argmin(axis=1)
+    u_front = uvw[:, np.arange(B), up, 0]
+    assert np.abs(u_front - ws[None]).max() > 0.05 and np.allclose(env0.state["u"][np.arange(B), 0, up].cpu().numpy(), ws, rtol=1e-6)
+
+
+def test_facade_with_mann_box_runs_and_meanders(built_lib):
+    from windgym_b200 import V80, WindFarmEnv
+    _, box = _boxes()
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    env = WindFarmEnv(V80(), config=cfg, turbtype="MannGenerate", turb_box=box, seed=2, device="cuda:0")
+    obs, info = env.reset(seed=2)
+    p = []
+    for _ in range(20):
+        obs, r, term, trunc, info = env.step(np.zeros(2, dtype=np.float32))
+        p.append(info["Power agent"])
+    assert np.isfinite(p).all() and np.std(p) > 1e-3 * np.mean(p)      # power fluctuates with the inflow
+    assert info["Turbulence intensity"] == env.ti and 0.02 <= env.ti <= 0.15
+    img_env = env.fs.get_windspeed(type("V", (), dict(x=np.linspace(-400, 800, 40), y=np.linspace(-200, 200, 30), z=70.0))())
+    assert np.std(img_env[2]) > 0                                       # w' present in the rendered field
+    env.close()

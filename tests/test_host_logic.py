@@ -70,7 +70,8 @@ def test_config_defaults_and_derived():
     ({"Track_power": True}, {}, NotImplementedError, "Track_power"),                                   # :168
     ({"BaseController": "PyWake"}, {}, ValueError, "BaseController must be either Local or Global"),  # :314
     ({}, dict(fill_window=-3), ValueError, "fill_window must be True or a non-negative integer"),     # :240
-    ({}, dict(turbtype="MannLoad"), NotImplementedError, "turbtype"),
+    ({}, dict(turbtype="Random"), NotImplementedError, "turbtype"),
+    ({}, dict(turbtype="Mann"), ValueError, "Invalid turbulence type"),                                # :666-668
 ])
 def test_config_errors_match_reference(patch, kw, exc, msg):
     cfg = small_config(2, 2, reward="Baseline", **patch)

@@ -13,7 +13,7 @@ def _sampler(site, n_envs, seed, **wind):
     env = VecWindFarmEnv.__new__(VecWindFarmEnv)
     w = dict(ws_min=4, ws_max=20, TI_min=0.02, TI_max=0.15, wd_min=200, wd_max=330)
     w.update(wind)
-    env.ec = types.SimpleNamespace(yaw_init_mode="Zeros", yaw_start=15.0, **w)
+    env.ec = types.SimpleNamespace(yaw_init_mode="Zeros", yaw_start=15.0, turbtype="None", **w)
     env.n_envs, env.n_turb, env.sample_site, env._site_tables = n_envs, 2, site, None
     env.ws, env.ti, env.wd = np.zeros(n_envs), np.zeros(n_envs), np.zeros(n_envs)
     env._wind_override, env._episode, env.yaw_initial = {}, 1, [0]

@@ -45,7 +45,8 @@ class Config(C.Structure):
 class ResetArgs(C.Structure):
     _fields_ = [("mask", C.c_void_p), ("ws", C.c_void_p), ("ti_flow", C.c_void_p), ("wd", C.c_void_p),
                 ("yaw0", C.c_void_p), ("rated_power", C.c_void_p), ("k_emit", C.c_void_p),
-                ("t_developed", C.c_void_p), ("time_max", C.c_void_p)]
+                ("t_developed", C.c_void_p), ("time_max", C.c_void_p), ("tb_offset", C.c_void_p),
+                ("tb_scale", C.c_void_p)]
 
 
 # every symbol include/windgym_b200.h declares: (restype, argtypes)
@@ -64,6 +65,8 @@ SYMBOLS = {
     "wg_flow_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_mes_push_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "wg_set_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_float, C.c_float]),
     "wg_flow_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_float, C.c_void_p, C.c_void_p]),
     "wg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

@@ -64,9 +64,11 @@ class EnvConfig:
         if self.dt_env % self.dt_sim != 0:
             raise ValueError("dt_env must be a multiple of dt_sim")
         self.S = int(self.dt_env / self.dt_sim)
-        if self.turbtype != "None":
-            # MannLoad / MannGenerate / MannFixed / Random need the turbulence-box row
-            raise NotImplementedError(f"turbtype={self.turbtype!r}: only the uniform-inflow 'None' site is built yet")
+        if self.turbtype == "Random":
+            raise NotImplementedError("turbtype='Random' (white-noise RandomTurbulence field) is not built; use a Mann "
+                                      "box type or 'None'")
+        if self.turbtype not in ("None", "MannLoad", "MannGenerate", "MannFixed"):
+            raise ValueError("Invalid turbulence type specified")  # Wind_Farm_Env.py:666-668
         self.yaw_start = 15.0
         self.d_particle = 0.2
         self.maxturbpower = float(max(t.power(np.arange(10, 25, 1))))

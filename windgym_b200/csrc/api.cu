@@ -104,6 +104,8 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.base_pow_mean = at<float>(state, h, "base_pow_mean");
   d.old_yaw = at<float>(state, h, "old_yaw");
   d.rings = at<float>(state, h, "rings");
+  d.tb_off = at<float>(state, h, "tb_off");
+  d.tb_scale = at<float>(state, h, "tb_scale");
   d.fp_ring = at<float>(state, h, "farm_pow_ring");
   d.bp_ring = at<float>(state, h, "base_pow_ring");
   return d;
@@ -299,6 +301,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "ord_sorted", 1, {B, T});
   add_field(h, "meas", 0, {B, 4, T});
   add_field(h, "old_yaw", 0, {B, T});
+  add_field(h, "tb_off", 0, {B, 3});
+  add_field(h, "tb_scale", 0, {B});
   add_field(h, "rings", 0, {B, off});
   add_field(h, "farm_pow_ring", 0, {B, cfg->power_avg});
   add_field(h, "base_pow_ring", 0, {B, cfg->power_avg});
@@ -372,8 +376,10 @@ int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, v
     return fail(WG_ERR_INVALID, "wg_reset: every per-env input array is required");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   wg::Dev d = bind(h, state);
+  if (h->dev.tb_raw && (!args->tb_offset || !args->tb_scale))
+    return fail(WG_ERR_INVALID, "wg_reset: a handle with a turbulence box needs tb_offset and tb_scale");
   wg::ResetDevArgs ra{args->mask, args->ws, args->ti_flow, args->wd, args->yaw0, args->rated_power,
-                      args->k_emit, args->t_developed, args->time_max};
+                      args->k_emit, args->t_developed, args->time_max, args->tb_offset, args->tb_scale};
   WG_LAUNCH(wg::launch_reset_init(d, ra, s), "wg_reset_init_kernel");
   // fs.run(t_developed) for the agent farm and the baseline farm (Wind_Farm_Env.py:734, :782)
   wg::FlowArgs spin{};
@@ -426,6 +432,27 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
   WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(step)");
   if (ev) cudaEventRecord(ev[2], s);
+  return WG_OK;
+}
+
+int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, int32_t nx, int32_t ny, int32_t nz,
+                      float dx, float dy, float dz) {
+  if (!h) return fail(WG_ERR_INVALID, "wg_set_turbulence: null argument");
+  wg::Dev& d = h->dev;
+  if (!raw_uvw0 && !lp_vw) {  // back to uniform inflow
+    d.tb_raw = nullptr; d.tb_lp = nullptr;
+    return WG_OK;
+  }
+  if (!raw_uvw0 || !lp_vw) return fail(WG_ERR_INVALID, "wg_set_turbulence: both box layouts are required");
+  if (nx < 2 || ny < 2 || nz < 2 || !(dx > 0.f) || !(dy > 0.f) || !(dz > 0.f))
+    return fail(WG_ERR_INVALID, "wg_set_turbulence: box needs >= 2 cells and positive spacing per axis");
+  if (((uintptr_t)raw_uvw0 & 15) || ((uintptr_t)lp_vw & 7))
+    return fail(WG_ERR_INVALID, "wg_set_turbulence: raw must be 16-byte and lp 8-byte aligned");
+  d.tb_raw = reinterpret_cast<const float4*>(raw_uvw0);
+  d.tb_lp = reinterpret_cast<const float2*>(lp_vw);
+  d.tb_n[0] = nx; d.tb_n[1] = ny; d.tb_n[2] = nz;
+  d.tb_inv_d[0] = 1.f / dx; d.tb_inv_d[1] = 1.f / dy; d.tb_inv_d[2] = 1.f / dz;
+  d.tb_len_x = (float)((double)nx * (double)dx);
   return WG_OK;
 }
 

@@ -276,6 +276,8 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
     d.ws[b] = a.ws[b]; d.ti[b] = a.ti[b]; d.wd[b] = a.wd[b]; d.rated[b] = a.rated[b];
     d.k_emit[b] = a.k_emit[b]; d.time_max[b] = a.time_max[b]; d.spin[b] = a.t_dev[b];
     d.timestep[b] = 0; d.n_push[b] = 0; d.flags[b] = 0; d.base_pow_mean[b] = 0.f;
+    for (int k = 0; k < 3; ++k) d.tb_off[b * 3 + k] = a.tb_off ? a.tb_off[b * 3 + k] : 0.f;
+    d.tb_scale[b] = a.tb_scale ? a.tb_scale[b] : 0.f;
     for (int f = 0; f < d.F; ++f) d.n_step[b * d.F + f] = 0;
   }
 }

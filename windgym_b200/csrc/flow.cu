@@ -61,6 +61,7 @@ struct __align__(16) FlowShared {
   float xr[TC], yr[TC], yaw[TC], u[TC], v[TC], w[TC], pw[TC], ct[TC], ind[TC], cg[TC], sg[TC];
   float xs[2 * TC];                         // turbine x sorted ascending, padded with +inf
   float sum_ws[TC], sum_wd[TC], sum_yaw[TC], sum_pw[TC];
+  float tu[TC], tv[TC], tw[TC];             // rotor-averaged ambient fluctuation (turbulence box)
   float acc_du[WG_NWARP][TC], acc_dv[WG_NWARP][TC];  // per-warp superposed deficit per rotor
   int ord[TC];                              // turbine index of xs[k]
   int head[TC], count[TC], pre[TC + 1], emit_slot[TC];
@@ -207,15 +208,16 @@ __device__ __forceinline__ void tab_interp2(const float* __restrict__ xs, const 
 }
 
 // new wake-centre position after one step (Hill-vortex self-induced velocity added to the ambient)
-__device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws, float dt, float& xn, float& yn,
-                                      float& zn, float& dx) {
+// tv = low-pass ambient (v', w') at the centre (meandering; zero for uniform inflow)
+__device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws, float dt, const float2 tv, float& xn,
+                                      float& yn, float& zn, float& dx) {
   float kd = K_HILL * (1.f - pm.w) * pc.x;
   float vx = ws - kd * pc.z;
-  float vy = kd * pc.w;
+  float vy = kd * pc.w + tv.x;
   dx = vx * dt;
   xn = pm.x + dx;
   yn = pm.y + vy * dt;
-  zn = pm.z;
+  zn = pm.z + tv.y * dt;
 }
 
 // Implicit Ainslie march of one profile row held in shared memory (oracle/dwm_numpy.py:ainslie_march).
@@ -466,7 +468,7 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
   }
 }
 
-template <int TC>
+template <int TC, bool TURB>
 __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // rows must be 256-byte aligned (XOR addressing)
   typedef FlowShared<TC> Shared;
@@ -549,6 +551,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
   int xs_top = 1;
   while (2 * xs_top - 1 < T) xs_top <<= 1;
   const float x_retire = xmax + MARGIN_D * d.D;
+  const float2 tv0 = make_float2(0.f, 0.f);
+  float tb_xo = 0.f, tb_yo = 0.f, tb_zo = 0.f, tb_sc = 0.f;
+  if (TURB) {
+    tb_xo = d.tb_off[b * 3 + 0]; tb_yo = d.tb_off[b * 3 + 1]; tb_zo = d.tb_off[b * 3 + 2];
+    tb_sc = d.tb_scale[b];
+  }
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
   float4* ha = sh.hit_a[warp];
@@ -557,6 +565,9 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
   for (int sub = 0; sub < nsteps; ++sub) {
     const float* __restrict__ pm_old = (nstep & 1) ? pmut1 : pmut0;
     float* __restrict__ pm_new = (nstep & 1) ? pmut0 : pmut1;
+    // Taylor shift of the turbulence box at the old time level (particle motion) and the new one (rotor inflow)
+    const float xs_t = TURB ? taylor_shift(d, ws, nstep, tb_xo) : 0.f;
+    const float xs_t1 = TURB ? taylor_shift(d, ws, nstep + 1, tb_xo) : 0.f;
 
     if (tid < T) {
       // baseline farm: greedy yaw controller before its flow step (BasicControllers.py:10-73, Wind_Farm_Env.py:949-952)
@@ -581,7 +592,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
         float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)tid * P + s) * 4));
         float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)tid * P + s) * 4));
         float xn, yn, zn, dx;
-        moved(pm, pc, ws, dt, xn, yn, zn, dx);
+        moved(pm, pc, ws, dt, tv0, xn, yn, zn, dx);  // only x matters here: the ambient (v', w') does not move it
         if (xn > x_retire) --cnt; else break;
       }
       sh.count[tid] = cnt;
@@ -644,7 +655,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
       }
       const uint32_t rowk = row_a ^ ((uint32_t)(Lc.slot & 7) << 4);
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
-      if (Lc.valid) moved(pmc, pcc, ws, dt, xn, yn, zn, dx);
+      if (Lc.valid) {
+        const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
+        moved(pmc, pcc, ws, dt, tvc, xn, yn, zn, dx);
+      }
       mbar_wait(bar, phase);
       phase ^= 1u;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
@@ -663,19 +677,19 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
       {
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        if (need_o) {
+        if (need_o || need_y) {
+          const float2 tvx = TURB ? sample_lp(d, pmx.x, pmx.y, pmx.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
-          moved(pmx, pcx, ws, dt, xo, yo, zo, dxx);
-        } else if (need_y) {
-          float dxx;
-          moved(pmx, pcx, ws, dt, xy, yy, zy, dxx);
+          if (need_o) moved(pmx, pcx, ws, dt, tvx, xo, yo, zo, dxx);
+          else moved(pmx, pcx, ws, dt, tvx, xy, yy, zy, dxx);
         }
         if (need_o && need_y) {  // rare: a one-station segment needs both neighbours from outside the tile
           const int sy = Lc.slot == P - 1 ? 0 : Lc.slot + 1;
           const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + sy) * 4));
           const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + sy) * 4));
+          const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
-          moved(pm, pc, ws, dt, xy, yy, zy, dxx);
+          moved(pm, pc, ws, dt, tvx, xy, yy, zy, dxx);
         }
         // Rotor planes bracketed by this station and its age neighbours: with c(x) = #{k : xs[k] < x} over the sorted
         // plane positions, plane k lies in [x1, x2) iff c(x1) <= k < c(x2).  Interval A = [self (younger end), older
@@ -740,6 +754,23 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
       sh.acc_du[warp][(lane + 32) % TC] = acc.du1;
       sh.acc_dv[warp][(lane + 32) % TC] = acc.dv1;
     }
+    if (TURB) {  // ambient fluctuation averaged over every rotor's quadrature points at the new time level
+      for (int idx = tid; idx < T * WG_NQ; idx += blockDim.x) {  // T*16: half-warps stay whole
+        const int t = idx >> 4;
+        const float4 q = sample_raw(d, sh.xr[t], fmaf(qy, R, sh.yr[t]), fmaf(qz, R, d.zh), xs_t1, tb_yo, tb_zo, tb_sc);
+        float qu = q.x, qv = q.y, qw = q.z;
+        const unsigned hm = 0xffffu << (lane & 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          qu += __shfl_xor_sync(hm, qu, o);
+          qv += __shfl_xor_sync(hm, qv, o);
+          qw += __shfl_xor_sync(hm, qw, o);
+        }
+        if ((lane & 15) == 0) {
+          sh.tu[t] = qu * (1.f / WG_NQ); sh.tv[t] = qv * (1.f / WG_NQ); sh.tw[t] = qw * (1.f / WG_NQ);
+        }
+      }
+    }
     bulk_wait_all0();
     fence_async_all();
     __syncthreads();
@@ -750,7 +781,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
       float du = 0.f, dv = 0.f;
 #pragma unroll
       for (int wi = 0; wi < WG_NWARP; ++wi) { du += sh.acc_du[wi][tid]; dv += sh.acc_dv[wi][tid]; }
-      const float u = ws - du, v = dv, w = 0.f;
+      const float u = ws - du + (TURB ? sh.tu[tid] : 0.f), v = dv + (TURB ? sh.tv[tid] : 0.f), w = TURB ? sh.tw[tid] : 0.f;
       const float yaw = sh.yaw[tid];
       float sg, cg;
       sincosf(yaw * 0.017453292519943295f, &sg, &cg);
@@ -852,21 +883,23 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
   }
 }
 
-template <int TC>
+template <int TC, bool TURB>
 static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
   const size_t smem = hdr_bytes<TC>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(wg_flow_kernel<TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e =
+        cudaFuncSetAttribute(wg_flow_kernel<TC, TURB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  wg_flow_kernel<TC><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  wg_flow_kernel<TC, TURB><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
 
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  return d.T <= 16 ? launch_as<16>(d, a, s) : launch_as<WG_MAX_T>(d, a, s);
+  if (d.tb_raw) return d.T <= 16 ? launch_as<16, true>(d, a, s) : launch_as<WG_MAX_T, true>(d, a, s);
+  return d.T <= 16 ? launch_as<16, false>(d, a, s) : launch_as<WG_MAX_T, false>(d, a, s);
 }
 
 }  // namespace wg

@@ -14,6 +14,8 @@
 
 namespace wg {
 
+struct Dev;
+
 constexpr float DR = 1.0f / 16.0f;
 constexpr float K_HILL = 0.4f;
 constexpr float K1 = 0.023f;
@@ -77,6 +79,13 @@ struct Dev {
   float *old_yaw;         // [B,T]
   float *rings;           // [B,ring_floats]
   float *fp_ring, *bp_ring;  // [B,power_avg]
+  // ambient turbulence box shared by all envs of the handle (null: uniform inflow); per-env offset and scale
+  const float4* tb_raw;   // [Nx,Ny,Nz] (u, v, w, 0)
+  const float2* tb_lp;    // [Nx,Ny,Nz] (v, w) low-pass filtered in y, z: moves the wake centres
+  int tb_n[3];
+  float tb_inv_d[3], tb_len_x;
+  float *tb_off;          // [B,3] position of the env inside the box [m]
+  float *tb_scale;        // [B]   scale_TI factor
 };
 
 struct FlowArgs {
@@ -99,7 +108,71 @@ struct ResetDevArgs {
   const uint8_t* mask;
   const float* ws; const float* ti; const float* wd; const float* yaw0; const float* rated;
   const int* k_emit; const int* t_dev; const int* time_max;
+  const float* tb_off; const float* tb_scale;
 };
+
+#ifdef __CUDACC__
+// Periodic trilinear sample of the frozen turbulence box at box coordinates (X, Y, Z) in cells.
+struct BoxIdx {
+  int i[2], j[2], k[2];
+  float fx, fy, fz;
+};
+__device__ __forceinline__ int wrap_cell(float fl, int n) {
+  int i = (int)fl % n;
+  return i < 0 ? i + n : i;
+}
+__device__ __forceinline__ BoxIdx box_index(const Dev& d, float X, float Y, float Z) {
+  BoxIdx b;
+  const float x0 = floorf(X), y0 = floorf(Y), z0 = floorf(Z);
+  b.fx = X - x0; b.fy = Y - y0; b.fz = Z - z0;
+  b.i[0] = wrap_cell(x0, d.tb_n[0]); b.i[1] = b.i[0] + 1 == d.tb_n[0] ? 0 : b.i[0] + 1;
+  b.j[0] = wrap_cell(y0, d.tb_n[1]); b.j[1] = b.j[0] + 1 == d.tb_n[1] ? 0 : b.j[0] + 1;
+  b.k[0] = wrap_cell(z0, d.tb_n[2]); b.k[1] = b.k[0] + 1 == d.tb_n[2] ? 0 : b.k[0] + 1;
+  return b;
+}
+// low-pass (v, w) at a wake centre; xs = Taylor shift U t - x_off (so that the box x is x - xs)
+__device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
+                                            float scale) {
+  const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
+  float v = 0.f, w = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float wt = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy) * (c ? b.fz : 1.f - b.fz);
+        const float2 q = __ldg(d.tb_lp + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2] + b.k[c]);
+        v = fmaf(wt, q.x, v);
+        w = fmaf(wt, q.y, w);
+      }
+  return make_float2(v * scale, w * scale);
+}
+__device__ __forceinline__ float4 sample_raw(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
+                                             float scale) {
+  const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
+  float u = 0.f, v = 0.f, w = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float wt = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy) * (c ? b.fz : 1.f - b.fz);
+        const float4 q = __ldg(d.tb_raw + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2] + b.k[c]);
+        u = fmaf(wt, q.x, u);
+        v = fmaf(wt, q.y, v);
+        w = fmaf(wt, q.z, w);
+      }
+  return make_float4(u * scale, v * scale, w * scale, 0.f);
+}
+// Taylor shift of the box at flow time t = n dt, reduced modulo the box length in double so that the float
+// coordinate stays small: box x = x - (U t - x_off)
+__device__ __forceinline__ float taylor_shift(const Dev& d, float ws, int n_step, float x_off) {
+  const double s = fmod((double)ws * (double)n_step * (double)d.dt - (double)x_off, (double)d.tb_len_x);
+  return (float)s;
+}
+#endif
 
 void set_rotor_points(const float* qy, const float* qz);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);

@@ -7,8 +7,9 @@ shapes and dtypes, info keys, and the attributes callers read (``AgentEval.py:83
 ``env.farm_measurements.get_*``.  All compute runs in the CUDA library; these classes only move one env's
 numbers to the host.  For throughput use ``VecWindFarmEnv`` directly.
 
-Conscious differences from the reference (SURVEY.md quirk ledger): ``turbtype`` defaults to ``"None"`` (Mann boxes
-are the f-1 row, not built yet: any other value raises ``NotImplementedError``); after truncation the env stays
+Conscious differences from the reference (SURVEY.md quirk ledger): ``turbtype`` defaults to ``"None"``; the Mann site
+types share ONE box per env object (generated at construction, not at every reset); ``"Random"`` raises
+``NotImplementedError``; after truncation the env stays
 usable (Q11); ``WindFarmEnvMulti`` constructs (Q9-i), declares the observation length it actually returns (Q9-ii)
 and keeps the reference's double ``timestep`` increment only with ``compat_double_timestep=True`` (Q9-iii).
 """
@@ -262,7 +263,7 @@ class WindFarmEnv(_GymEnv):
     def __init__(self, turbine, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.50, TurbBox="Default", turbtype="None",
                  yaml_path=None, Baseline_comp=False, yaw_init=None, render_mode=None, seed=None, dt_sim=1, dt_env=1,
                  yaw_step=1, fill_window=True, sample_site=None, HTC_path=None, reset_init=True, config=None,
-                 device="cuda:0"):
+                 device="cuda:0", turb_box=None):
         if HTC_path is not None:
             raise NotImplementedError("HAWC2 turbines (HTC_path) are out of scope: external aero-elastic co-simulation")
         if render_mode is not None and render_mode not in self.metadata["render_modes"]:
@@ -272,7 +273,8 @@ class WindFarmEnv(_GymEnv):
                                   TI_min_mes=TI_min_mes, TI_max_mes=TI_max_mes, TurbBox=TurbBox, turbtype=turbtype,
                                   Baseline_comp=Baseline_comp, yaw_init=yaw_init, seed=seed, dt_sim=dt_sim,
                                   dt_env=dt_env, yaw_step=yaw_step, fill_window=fill_window, device=device,
-                                  multi_agent=self._multi_agent, eval_mode=self._eval_mode, sample_site=sample_site)
+                                  multi_agent=self._multi_agent, eval_mode=self._eval_mode, sample_site=sample_site,
+                                  turb_box=turb_box)
         self.sample_site = sample_site
         v, ec = self.vec, self.vec.ec
         self.turbine, self.seed = turbine, seed
@@ -415,11 +417,12 @@ class FarmEval(WindFarmEnv):
 
     def __init__(self, turbine, TI_min_mes=0.0, TI_max_mes=0.50, yaw_init="Zeros", TurbBox="Default", yaml_path=None,
                  Baseline_comp=False, render_mode=None, turbtype="None", seed=None, dt_sim=1, dt_env=1, yaw_step=1,
-                 n_passthrough=5, HTC_path=None, reset_init=True, config=None, device="cuda:0"):
+                 n_passthrough=5, HTC_path=None, reset_init=True, config=None, device="cuda:0", turb_box=None):
         super().__init__(turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes, TI_max_mes=TI_max_mes,
                          TurbBox=TurbBox, turbtype=turbtype, yaml_path=yaml_path, Baseline_comp=Baseline_comp,
                          yaw_init=yaw_init, render_mode=render_mode, seed=seed, dt_sim=dt_sim, dt_env=dt_env,
-                         yaw_step=yaw_step, HTC_path=HTC_path, reset_init=reset_init, config=config, device=device)
+                         yaw_step=yaw_step, HTC_path=HTC_path, reset_init=reset_init, config=config, device=device,
+                         turb_box=turb_box)
 
     def set_wind_vals(self, ws=None, ti=None, wd=None):
         self.vec.set_wind_vals(ws=ws, ti=ti, wd=wd)
@@ -432,7 +435,10 @@ class FarmEval(WindFarmEnv):
         self.vec.set_yaw_vals(yaw_vals)
 
     def update_tf(self, path):
-        raise NotImplementedError("turbulence boxes are the f-1 row of SURVEY.md section 8 (not built yet)")
+        """FarmEval.update_tf (FarmEval.py:86-90): pin the turbulence box file used from the next reset on."""
+        if self.vec.ec.turbtype == "None":
+            raise ValueError("update_tf needs a Mann turbtype (MannLoad)")
+        self.vec._attach_turbulence(None, path)
 
 
 class WindFarmEnvMulti(WindFarmEnv):
@@ -445,14 +451,14 @@ class WindFarmEnvMulti(WindFarmEnv):
     def __init__(self, turbine, n_passthrough=20, TI_min_mes=0.0, TI_max_mes=0.50, TurbBox="Default", turbtype="None",
                  yaml_path=None, Baseline_comp=False, yaw_init=None, render_mode=None, seed=None, dt_sim=1, dt_env=1,
                  yaw_step=1, fill_window=True, sample_site=None, config=None, device="cuda:0",
-                 compat_double_timestep=False):
+                 compat_double_timestep=False, turb_box=None):
         self.compat_double_timestep = compat_double_timestep
         self.possible_agents, self.agents = [], []
         super().__init__(turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes, TI_max_mes=TI_max_mes,
                          TurbBox=TurbBox, turbtype=turbtype, yaml_path=yaml_path, Baseline_comp=Baseline_comp,
                          yaw_init=yaw_init, render_mode=None, seed=seed, dt_sim=dt_sim, dt_env=dt_env,
                          yaw_step=yaw_step, fill_window=fill_window, sample_site=sample_site, reset_init=False,
-                         config=config, device=device)
+                         config=config, device=device, turb_box=turb_box)
         self.possible_agents = ["turbine_" + str(r) for r in range(self.n_turb)]
         self.agent_name_mapping = dict(zip(self.possible_agents, range(self.n_turb)))
         self.reset(seed=seed)

@@ -24,7 +24,7 @@ class VecWindFarmEnv:
     def __init__(self, turbine, n_envs, yaml_path=None, config=None, n_passthrough=5, TI_min_mes=0.0,
                  TI_max_mes=0.50, TurbBox="Default", turbtype="None", Baseline_comp=False, yaw_init=None,
                  seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True, device="cuda:0",
-                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None):
+                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None, turb_box=None):
         cfg = config if config is not None else load_yaml(yaml_path)
         self.ec = ec = EnvConfig(cfg, turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes,
                                  TI_max_mes=TI_max_mes, turbtype=turbtype, Baseline_comp=Baseline_comp,
@@ -49,6 +49,9 @@ class VecWindFarmEnv:
         self.lib = _lib.load()
         torch.cuda.set_device(self.device)
         self._create()
+        self.turb_box = None
+        if ec.turbtype != "None":
+            self._attach_turbulence(turb_box, TurbBox)
         self.obs_shape = (self.n_envs, self.n_turb, self.obs_var) if multi_agent else (self.n_envs, self.obs_var)
         self.obs = torch.zeros(self.obs_shape, dtype=torch.float32, device=self.device)
         self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
@@ -119,6 +122,37 @@ class VecWindFarmEnv:
             self.state[nm.decode()] = self._state[off.value:off.value + n].view(_TORCH_DT[dt.value]).view(shape)
             i += 1
 
+    def _attach_turbulence(self, box, TurbBox):
+        """``_def_site`` (Wind_Farm_Env.py:598-678) for the Mann site types.  ONE box per handle, shared read-only by
+        all envs of the GPU; each env sits at its own offset inside the periodic box and carries its own
+        ``scale_TI`` factor (the batched counterpart of one box per env).  ``turb_box`` injects a ready ``MannBox``
+        (what the reference's tests do by patching ``MannTurbulenceField.generate``, tests/test_basics.py:56-63)."""
+        import glob
+        import os
+        from .mann import MannBox
+        ec = self.ec
+        if box is None:
+            if ec.turbtype == "MannFixed":      # :647-656
+                box = MannBox.generate(0.1, 33.6, 3.9, Nxyz=(2048, 512, 64), dxyz=(3.0, 3.0, 3.0), seed=1234,
+                                       device=self.device, lowpass_width=2 * ec.D)
+            elif ec.turbtype == "MannGenerate":  # :621-637
+                box = MannBox.generate(0.1, 33.6, 3.9, Nxyz=(4096, 512, 64), dxyz=(ec.D / 20, ec.D / 10, ec.D / 10),
+                                       seed=0 if self.seed is None else int(self.seed), device=self.device,
+                                       lowpass_width=2 * ec.D)
+            else:                                 # MannLoad, :612-617: one of the files under TurbBox
+                files = [TurbBox] if os.path.isfile(str(TurbBox)) else sorted(
+                    f for ext in ("*.npz", "*.npy", "*.nc") for f in glob.glob(os.path.join(str(TurbBox), ext)))
+                if not files:
+                    raise FileNotFoundError(f"TurbBox={TurbBox!r}: no turbulence box file (.npz/.npy/.nc) found")
+                pick = np.random.default_rng(self.seed).choice(len(files))
+                box = MannBox.from_file(files[pick], device=self.device, lowpass_width=2 * ec.D)
+        if box.device != self.device:
+            raise ValueError(f"turbulence box lives on {box.device}, env on {self.device}")
+        self.turb_box = box
+        nx, ny, nz = box.Nxyz
+        _lib.check(self.lib.wg_set_turbulence(self._h, _ptr(box.raw), _ptr(box.lp), nx, ny, nz, *box.dxyz))
+        self.turb_offset = np.zeros((self.n_envs, 3))
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.wg_destroy(self._h)
@@ -166,6 +200,8 @@ class VecWindFarmEnv:
         single env's first episode, which is what gymnasium seeds the reference with."""
         ec, B, T = self.ec, self.n_envs, self.n_turb
         envs = range(B) if envs is None else envs
+        if not hasattr(self, "_tf_seed"):
+            self._tf_seed = np.zeros(B, dtype=np.int64)
         ws, ti, wd = self.ws.copy(), self.ti.copy(), self.wd.copy()
         yaw0 = np.zeros((B, T))
         for i in envs:
@@ -186,6 +222,8 @@ class VecWindFarmEnv:
                 wd[i] = np.clip(wd_s, ec.wd_min, ec.wd_max)
                 ws[i] = np.clip(ws_s, ec.ws_min, ec.ws_max)
                 ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
+            if ec.turbtype == "MannGenerate":    # TF_seed draw sits between wd and yaw (Wind_Farm_Env.py:623)
+                self._tf_seed[i] = int(rng.integers(0, 100000))
             if ec.yaw_init_mode == "Random":
                 yaw0[i] = rng.uniform(low=-ec.yaw_start, high=ec.yaw_start, size=T)
         for k, arr in (("ws", ws), ("ti", ti), ("wd", wd)):
@@ -211,9 +249,10 @@ class VecWindFarmEnv:
                                  np.asarray(lw.Weibull_k_ilk)[0, :, 0].astype(np.float64), freqs / freqs.sum())
         return self._site_tables
 
-    def reset(self, seed=None, mask=None, wind=None, yaw0=None):
+    def reset(self, seed=None, mask=None, wind=None, yaw0=None, turb_offset=None):
         """WindFarmEnv.reset for the masked envs (all when ``mask`` is None).
-        ``wind=(ws, ti, wd)`` and ``yaw0`` ([B,T]) inject conditions instead of sampling them."""
+        ``wind=(ws, ti, wd)`` and ``yaw0`` ([B,T]) inject conditions instead of sampling them; ``turb_offset``
+        ([B,3] metres) pins the envs' positions inside the turbulence box."""
         ec, B, T, dev = self.ec, self.n_envs, self.n_turb, self.device
         sel = np.arange(B) if mask is None else np.flatnonzero(np.asarray(mask))
         if seed is None:
@@ -228,17 +267,31 @@ class VecWindFarmEnv:
         n_spin, time_max, k_emit = ec.reset_integers(ws, wd)
         rated = np.asarray(self.turbine.power(ws), dtype=np.float64)
         ti_flow = np.zeros(B)  # turbtype "None": RandomTurbulence(ti=0) (Wind_Farm_Env.py:661-665)
+        tb = {}
+        if self.turb_box is not None:
+            ti_flow = ti.copy()    # TurbulenceFieldSite over a box scaled to the episode's TI (:617,:638,:657)
+            if turb_offset is not None:
+                self.turb_offset[sel] = np.broadcast_to(np.asarray(turb_offset, dtype=np.float64), (B, 3))[sel]
+            elif B > 1:            # a lone env sits at the box origin like the reference's single simulation
+                L = np.array(self.turb_box.Nxyz) * np.array(self.turb_box.dxyz)
+                for i in sel:
+                    r = np.random.default_rng([0 if seed is None else int(seed), int(i), self._episode,
+                                               int(self._tf_seed[i]), 12345])
+                    self.turb_offset[i] = r.uniform(0.0, L)
+            tb = dict(off=self.turb_offset, scale=self.turb_box.scale_for(ti, ws))
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
         i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev, non_blocking=True)
         keep = dict(ws=f32(ws), ti=f32(ti_flow), wd=f32(wd), yaw0=f32(y0), rated=f32(rated), k=i32(k_emit),
-                    spin=i32(n_spin), tmax=i32(time_max))
+                    spin=i32(n_spin), tmax=i32(time_max), tb_off=f32(tb["off"]) if tb else None,
+                    tb_scale=f32(tb["scale"]) if tb else None)
         m = None
         if mask is not None:
             m = torch.as_tensor(np.ascontiguousarray(np.asarray(mask), dtype=np.uint8)).to(dev)
             keep["mask"] = m
         args = _lib.ResetArgs(mask=_ptr(m), ws=_ptr(keep["ws"]), ti_flow=_ptr(keep["ti"]), wd=_ptr(keep["wd"]),
                               yaw0=_ptr(keep["yaw0"]), rated_power=_ptr(keep["rated"]), k_emit=_ptr(keep["k"]),
-                              t_developed=_ptr(keep["spin"]), time_max=_ptr(keep["tmax"]))
+                              t_developed=_ptr(keep["spin"]), time_max=_ptr(keep["tmax"]),
+                              tb_offset=_ptr(keep["tb_off"]), tb_scale=_ptr(keep["tb_scale"]))
         _lib.check(self.lib.wg_reset(self._h, _ptr(self._state), C.byref(args), _ptr(self.obs), self._stream()))
         self._keep = keep  # inputs stay alive until the stream has consumed them
         self._episode += 1
