@@ -194,10 +194,13 @@ def run_reference(a):
 def bench_config(a, envs_per_rank, where):
     return {"workload": f"BASELINE.json configs[1]: {a.nx * a.ny}-turbine {a.nx}x{a.ny} grid (V80, reference linspace "
                         f"layout), {envs_per_rank} envs per {'GPU' if where == 'gpu' else 'step (one per host core)'}, "
-                        "yaw-only actions U(-1,1), Env1.yaml obs/yaw semantics, turbtype None (uniform inflow)",
+                        "yaw-only actions U(-1,1), Env1.yaml obs/yaw semantics, " +
+                        ("turbtype None (uniform inflow)" if getattr(a, "turbtype", "None") == "None" else
+                         "Mann turbulence box 1024x128x32 @ 3 m shared by the envs"),
             "n_turb": a.nx * a.ny, "envs_per_gpu": envs_per_rank if where == "gpu" else None,
             "farms_per_env": 2 if a.reward == "Baseline" else 1, "power_reward": a.reward,
             "dt_env": 1, "dt_sim": 1, "obs_dim": 2 * a.nx * a.ny, "parallelism": f"env-sharded x{a.gpus}",
+            "turbtype": getattr(a, "turbtype", "None"),
             "l2_policy": "working set (wake state, GBs per step) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -217,6 +220,9 @@ def run_gpu(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as g
@@ -234,7 +240,12 @@ def run_gpu(a):
     n_pass = n_passthrough_for(total, cfg)
     env_ids = np.arange(rank * B, (rank + 1) * B)
     ws, ti, wd, yaw0 = sample_conditions(cfg, env_ids, T)
-    env = VecWindFarmEnv(V80(), B, config=cfg, device=str(dev), n_passthrough=n_pass)
+    kw = {}
+    if a.turbtype == "Mann":   # ambient turbulence: the reference tests' reduced box (tests/test_basics.py:38-45)
+        from windgym_b200.mann import MannBox
+        kw = dict(turbtype="MannFixed", turb_box=MannBox.generate(0.1, 33.6, 3.9, Nxyz=(1024, 128, 32), dxyz=(3.0, 3.0, 3.0),
+                                                                  seed=1234, device=str(dev)))
+    env = VecWindFarmEnv(V80(), B, config=cfg, device=str(dev), n_passthrough=n_pass, seed=rank, **kw)
     env.reset(wind=(ws, ti, wd), yaw0=yaw0)
     torch.cuda.synchronize()
     assert int(np.min(env.time_max)) > total, "episode would truncate inside the run"
@@ -305,6 +316,8 @@ def run_gpu(a):
     env.profile_enable(False)
     live = int(env.state["count"].sum().item())          # live wake stations of this rank (all envs, farms, chains)
     F, S = env.n_farms, env.ec.S
+    # with a turbulence box every station also gathers 8 corners x 8 B of the low-pass box (not counted as
+    # algorithmic state traffic: the box is shared and L2-resident at this size)
     bytes_flow = S * (live * STATION_BYTES + B * F * T * TURB_BYTES)
     t_flow = flow_ms / max(n_prof, 1) * 1e-3
     env.check_flags()
@@ -360,6 +373,8 @@ def main():
     ap.add_argument("--reward", default="Power_avg", choices=["Power_avg", "Baseline"],
                     help="Baseline adds the second (greedy-controller) farm per env: 2x the flow work")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--turbtype", default="None", choices=["None", "Mann"],
+                    help="Mann: ambient Mann turbulence box (meandering + rotor fluctuations); not the headline config")
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3)
     if a.impl == "reference":
