@@ -35,8 +35,8 @@
 namespace wg {
 
 #define WG_NWARP 4        // warps per CTA (one per 32-lane TMEM quarter)
-#define WG_HIT_CAP 64     // per-warp hit list entries (one detection pass adds at most 2 x 32)
-#define WG_TAB_CAP 64     // P/CT table knots staged in shared memory (longer tables are read from global)
+#define WG_HIT_CAP 32     // per-warp hit list entries (one detection pass of one interval kind adds at most 32)
+#define WG_TAB_CAP 32     // P/CT table knots staged in shared memory (longer tables are read from global)
 #define WG_TMEM_COLS 64
 
 __constant__ float c_qy[WG_NQ];
@@ -54,27 +54,28 @@ void set_rotor_points(const float* qy, const float* qz) {
 }
 
 // Per-CTA bookkeeping in front of the tile buffers.  TC = turbine capacity of the tables (16 or WG_MAX_T: small
-// farms leave the shared memory to more resident CTAs).
-template <int TC>
+// farms leave the shared memory to more resident CTAs -- with TC = 16 the CTA needs 37 KB, six fit on an SM).
+template <int TC, bool TURB>
 struct __align__(16) FlowShared {
   unsigned long long mbar[WG_NWARP];
   float xr[TC], yr[TC], yaw[TC], u[TC], v[TC], w[TC], pw[TC], ct[TC], ind[TC], cg[TC], sg[TC];
   float xs[2 * TC];                         // turbine x sorted ascending, padded with +inf
   float sum_ws[TC], sum_wd[TC], sum_yaw[TC], sum_pw[TC];
-  float tu[TC], tv[TC], tw[TC];             // rotor-averaged ambient fluctuation (turbulence box)
+  float tu[TURB ? TC : 1], tv[TURB ? TC : 1], tw[TURB ? TC : 1];  // rotor-averaged ambient fluctuation
   float acc_du[WG_NWARP][TC], acc_dv[WG_NWARP][TC];  // per-warp superposed deficit per rotor
   int ord[TC];                              // turbine index of xs[k]
   int head[TC], count[TC], pre[TC + 1], emit_slot[TC];
   float base_sum;
   uint32_t tmem_base;                       // TMEM allocation of the CTA
-  int pad[1];
   float tab_ws[WG_TAB_CAP], tab_p[WG_TAB_CAP], tab_ct[WG_TAB_CAP];
   float4 hit_a[WG_NWARP][WG_HIT_CAP];       // w*U0e*cos g0, w*U0e*sin g0, ry, rz
-  int2 hit_b[WG_NWARP][WG_HIT_CAP];         // shared address of the row ^ (key << 4), rotor index j
+  uint32_t hit_b[WG_NWARP][WG_HIT_CAP];     // (shared address of the row ^ (key << 4)) | rotor index j << 20
 };
 
-template <int TC>
-__host__ __device__ constexpr size_t hdr_bytes() { return (sizeof(FlowShared<TC>) + 255) / 256 * 256; }
+template <int TC, bool TURB>
+__host__ __device__ constexpr size_t hdr_bytes() { return (sizeof(FlowShared<TC, TURB>) + 255) / 256 * 256; }
+// six CTAs per SM: 6 x (header + 32 KB of tiles + 1 KB reserved) must fit the 228 KB of the SM
+static_assert(hdr_bytes<16, false>() <= 5120 && hdr_bytes<16, true>() <= 5120, "small-farm header outgrew 5 KB");
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -436,7 +437,7 @@ struct RotorAcc {
 // Evaluate the queued (station row, rotor) hits of one warp: two hits per pass, 16 quadrature points each on
 // 16 lanes, shuffle-reduced to the rotor average.
 template <int TC>
-__device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const int2* __restrict__ hb, int nh,
+__device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const uint32_t* __restrict__ hb, int nh,
                                            RotorAcc<TC>& acc, int lane, float qy, float qz) {
   const unsigned full = 0xffffffffu;
   const int half = lane >> 4;
@@ -444,13 +445,14 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
     const bool ok = h0 + half < nh;
     const int h = ok ? h0 + half : h0;
     const float4 a = ha[h];
-    const int2 b = hb[h];
+    const uint32_t bp = hb[h], brow = bp & 0xfffffu;
+    const int bj = (int)(bp >> 20);
     const float dy = a.z + qy, dz = a.w + qz;
     const float s = sqrt_fast(fmaf(dy, dy, dz * dz)) * (1.f / DR);
     const int j0 = min((int)s, WG_NR - 2);
     const float fr = s - (float)j0;
-    const float u0 = lds1((uint32_t)b.x ^ ((uint32_t)j0 << 2));
-    float u1 = lds1((uint32_t)b.x ^ ((uint32_t)(j0 + 1) << 2));
+    const float u0 = lds1(brow ^ ((uint32_t)j0 << 2));
+    float u1 = lds1(brow ^ ((uint32_t)(j0 + 1) << 2));
     if (j0 == WG_NR - 2) u1 = 1.f;
     float d = fmaf(fr, u0 - u1, 1.f - u0);  // (1-u0)(1-fr) + (1-u1) fr
     if (s >= (float)(WG_NR - 1) || !ok) d = 0.f;
@@ -462,16 +464,16 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
     const float du = a.x * d, dv = a.y * d;
     const float duA = __shfl_sync(full, du, 0), dvA = __shfl_sync(full, dv, 0);
     const float duB = __shfl_sync(full, du, 16), dvB = __shfl_sync(full, dv, 16);
-    const int jA = __shfl_sync(full, b.y, 0), jB = __shfl_sync(full, b.y, 16);
+    const int jA = __shfl_sync(full, bj, 0), jB = __shfl_sync(full, bj, 16);
     acc.add(lane, jA, duA, dvA);
     acc.add(lane, jB, duB, dvB);  // a padded second hit carries d = 0
   }
 }
 
 template <int TC, bool TURB>
-__global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, const FlowArgs a) {
+__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // rows must be 256-byte aligned (XOR addressing)
-  typedef FlowShared<TC> Shared;
+  typedef FlowShared<TC, TURB> Shared;
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int T = d.T, P = d.P, F = d.F;
 
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
   float* pmut0 = d.pmut + (size_t)bf * T * P * 4;
   float* pmut1 = pmut0 + (size_t)d.B * F * T * P * 4;
   // this warp's tile buffer (32 rows x 256 B) and this lane's row, as shared addresses
-  const uint32_t tile_a = smem_u32(smem_raw + hdr_bytes<TC>()) + (uint32_t)warp * WG_TILE * WG_ROW_BYTES;
+  const uint32_t tile_a = smem_u32(smem_raw + hdr_bytes<TC, TURB>()) + (uint32_t)warp * WG_TILE * WG_ROW_BYTES;
   const uint32_t row_a = tile_a + (uint32_t)lane * WG_ROW_BYTES;
   const float qy = c_qy[lane & 15], qz = c_qz[lane & 15];
   void* bar = &sh.mbar[warp];
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
   const unsigned full = 0xffffffffu;
   const unsigned lt = (1u << lane) - 1u;
   float4* ha = sh.hit_a[warp];
-  int2* hb = sh.hit_b[warp];
+  uint32_t* hb = sh.hit_b[warp];
 
   for (int sub = 0; sub < nsteps; ++sub) {
     const float* __restrict__ pm_old = (nstep & 1) ? pmut1 : pmut0;
@@ -610,83 +612,80 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
     // ------------------------------------------------------------------ warp-private tile pipeline
     RotorAcc<TC> acc;
     acc.clear();
-    LaneLoc Ln;
-    Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
-    float4 pmn = make_float4(0.f, 0.f, 0.f, 0.f), pcn = pmn;  // station scalars of the NEXT tile (register prefetch)
-    if (warp < ntiles) {
-      Ln = locate(sh, warp, lane, T, P, ntot);
-      if (Ln.valid) {
-        pmn = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Ln.chain * P + Ln.slot) * 4));
-        pcn = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Ln.chain * P + Ln.slot) * 4));
-      }
-    }
     for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
-      const LaneLoc Lc = Ln;
-      const float4 pmc = pmn, pcc = pcn;
+      const LaneLoc Lc = locate(sh, tile, lane, T, P, ntot);
       const Seg sg = segments(Lc, lane);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)sg.nvalid * WG_ROW_BYTES);
       __syncwarp();
-      float* gsrc = prof + ((size_t)Lc.chain * P + Lc.slot) * WG_NR;
-      if (sg.start) bulk_g2s(row_a, gsrc, (uint32_t)sg.len * WG_ROW_BYTES, bar);
-      // age neighbours outside this tile (older = flat index - 1 of the same chain, younger = + 1): issue their
-      // scalar loads now, they are consumed after the march
+      const size_t st_c = (size_t)Lc.chain * P + Lc.slot;
+      if (sg.start) bulk_g2s(row_a, prof + st_c * WG_NR, (uint32_t)sg.len * WG_ROW_BYTES, bar);
+      // station scalars: in flight together with the tile, consumed after the mbarrier wait
+      float4 pmc = make_float4(0.f, 0.f, 0.f, 0.f), pcc = pmc;
+      if (Lc.valid) {
+        pmc = __ldcg(reinterpret_cast<const float4*>(pm_old + st_c * 4));
+        pcc = __ldcg(reinterpret_cast<const float4*>(pcon + st_c * 4));
+      }
+      // age neighbours outside this tile (older = flat index - 1 of the same chain, younger = + 1): pull their
+      // scalars towards L2 now, they are loaded after the march
       const int ch_o = __shfl_up_sync(full, Lc.chain, 1), ch_y = __shfl_down_sync(full, Lc.chain, 1);
       const int vy_ = __shfl_down_sync(full, Lc.valid, 1);
       const bool has_o = Lc.valid && Lc.q > 0;
       const bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
       const bool need_o = has_o && (lane == 0 || ch_o != Lc.chain);
       const bool need_y = has_y && (lane == 31 || !vy_ || ch_y != Lc.chain);
-      float4 pmx = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pmx;  // the out-of-tile neighbour (older one if both)
       if (need_o || need_y) {
         const int sx = need_o ? (Lc.slot == 0 ? P - 1 : Lc.slot - 1) : (Lc.slot == P - 1 ? 0 : Lc.slot + 1);
-        pmx = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + sx) * 4));
-        pcx = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + sx) * 4));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + ((size_t)Lc.chain * P + sx) * 4));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + ((size_t)Lc.chain * P + sx) * 4));
       }
-      // while the tile is in flight: find the next one, fetch its scalars and pull its rows towards L2
-      const int nt = tile + WG_NWARP;
-      if (nt < ntiles) {
-        Ln = locate(sh, nt, lane, T, P, ntot);
+      // while the tile is in flight: pull the next tile's rows and scalars towards L2
+      if (tile + WG_NWARP < ntiles) {
+        const LaneLoc Ln = locate(sh, tile + WG_NWARP, lane, T, P, ntot);
         if (Ln.valid) {
           const size_t st = (size_t)Ln.chain * P + Ln.slot;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + st * WG_NR));
-          pmn = __ldcg(reinterpret_cast<const float4*>(pm_old + st * 4));
-          pcn = __ldcg(reinterpret_cast<const float4*>(pcon + st * 4));
+          if (lane == 0 || (Ln.slot & 7) == 0) {  // the station scalars: one 128-byte line per 8 slots
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st * 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st * 4));
+          }
         }
       }
       const uint32_t rowk = row_a ^ ((uint32_t)(Lc.slot & 7) << 4);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
       if (Lc.valid) {
         const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
         moved(pmc, pcc, ws, dt, tvc, xn, yn, zn, dx);
       }
-      mbar_wait(bar, phase);
-      phase ^= 1u;
+      const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
         const float ucn = march_row_tmem(rowk, taddr, dx * rR, xt_mid, pcc.y);
-        if (Lc.valid)
-          *reinterpret_cast<float4*>(pm_new + ((size_t)Lc.chain * P + Lc.slot) * 4) = make_float4(xn, yn, zn, ucn);
+        if (Lc.valid) *reinterpret_cast<float4*>(pm_new + st_c * 4) = make_float4(xn, yn, zn, ucn);
       }
       fence_async_smem();
       __syncwarp();
       if (sg.start) {  // write the marched rows back (same segments as the load)
-        bulk_s2g(gsrc, row_a, (uint32_t)sg.len * WG_ROW_BYTES);
+        bulk_s2g(prof + st_c * WG_NR, row_a, (uint32_t)sg.len * WG_ROW_BYTES);
         bulk_commit();
       }
       // ---- superposition: which rotor planes does this station bracket together with its age neighbours?
       {
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        if (need_o || need_y) {
-          const float2 tvx = TURB ? sample_lp(d, pmx.x, pmx.y, pmx.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
+        if (need_o) {
+          const size_t sx = (size_t)Lc.chain * P + (Lc.slot == 0 ? P - 1 : Lc.slot - 1);
+          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4));
+          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4));
+          const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
-          if (need_o) moved(pmx, pcx, ws, dt, tvx, xo, yo, zo, dxx);
-          else moved(pmx, pcx, ws, dt, tvx, xy, yy, zy, dxx);
+          moved(pm, pc, ws, dt, tvx, xo, yo, zo, dxx);
         }
-        if (need_o && need_y) {  // rare: a one-station segment needs both neighbours from outside the tile
-          const int sy = Lc.slot == P - 1 ? 0 : Lc.slot + 1;
-          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)Lc.chain * P + sy) * 4));
-          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)Lc.chain * P + sy) * 4));
+        if (need_y) {
+          const size_t sx = (size_t)Lc.chain * P + (Lc.slot == P - 1 ? 0 : Lc.slot + 1);
+          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4));
+          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4));
           const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
           moved(pm, pc, ws, dt, tvx, xy, yy, zy, dxx);
@@ -711,34 +710,42 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
         const int a_lo = min(cn, co), nA = abs(cn - co), b_lo = min(cn, cy), nB = abs(cn - cy);
         const int nmax = __reduce_max_sync(full, max(nA, nB));
         if (nmax > 0) {
-          const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
           const float rdA = rcp_fast(xo - xn), rdB = rcp_fast(xn - xy);
           for (int it = 0; it < nmax; ++it) {
-            const int kA = a_lo + it, kB = b_lo + it;
-            const int jA = it < nA ? sh.ord[kA] : Lc.chain, jB = it < nB ? sh.ord[kB] : Lc.chain;
-            const bool hitA = jA != Lc.chain, hitB = jB != Lc.chain;
-            const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
-            if (hitA) {
-              const float w = (sh.xs[kA] - xn) * rdA;
-              const float wg = kA >= cn ? 1.f - w : w - 1.f;
-              const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
-              const int p = __popc(mA & lt);
-              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
-              hb[p] = make_int2((int)rowk, jA);
+            {  // interval A hits of this pass
+              const int kA = a_lo + it;
+              const int jA = it < nA ? sh.ord[kA] : Lc.chain;
+              const bool hitA = jA != Lc.chain;
+              const unsigned mA = __ballot_sync(full, hitA);
+              if (hitA) {
+                const float w = (sh.xs[kA] - xn) * rdA;
+                const float wg = kA >= cn ? 1.f - w : w - 1.f;
+                const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
+                const int p = __popc(mA & lt);
+                ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
+                hb[p] = rowk | ((uint32_t)jA << 20);
+              }
+              __syncwarp();
+              if (mA) flush_hits<TC>(ha, hb, __popc(mA), acc, lane, qy, qz);
+              __syncwarp();
             }
-            const int nhA = __popc(mA);
-            if (hitB) {
-              const float w = (sh.xs[kB] - xy) * rdB;
-              const float wg = kB >= cy ? w : -w;
-              const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
-              const int p = nhA + __popc(mB & lt);
-              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
-              hb[p] = make_int2((int)rowk, jB);
+            {  // interval B hits of this pass
+              const int kB = b_lo + it;
+              const int jB = it < nB ? sh.ord[kB] : Lc.chain;
+              const bool hitB = jB != Lc.chain;
+              const unsigned mB = __ballot_sync(full, hitB);
+              if (hitB) {
+                const float w = (sh.xs[kB] - xy) * rdB;
+                const float wg = kB >= cy ? w : -w;
+                const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
+                const int p = __popc(mB & lt);
+                ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
+                hb[p] = rowk | ((uint32_t)jB << 20);
+              }
+              __syncwarp();
+              if (mB) flush_hits<TC>(ha, hb, __popc(mB), acc, lane, qy, qz);
+              __syncwarp();
             }
-            const int nh = nhA + __popc(mB);
-            __syncwarp();
-            if (nh > 0) flush_hits<TC>(ha, hb, nh, acc, lane, qy, qz);
-            __syncwarp();
           }
         }
       }
@@ -885,7 +892,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, 5) wg_flow_kernel(const Dev d, 
 
 template <int TC, bool TURB>
 static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  const size_t smem = hdr_bytes<TC>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES;
+  const size_t smem = hdr_bytes<TC, TURB>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
