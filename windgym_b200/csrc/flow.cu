@@ -338,14 +338,18 @@ __device__ __forceinline__ float march_row_tmem(uint32_t rowk, uint32_t taddr, f
       cq1 = tmem_ld4(taddr + 4 * max(c - 2, 0));
       cq0 = tmem_ld4(taddr + 4 * max(c - 3, 0));
       float ov[8];
-      const float jb = 2.f * (float)(c - 1);  // j/2 of the pair's first node
+      // sum_e (jb + e/2)(1 - u_e) = jb (8 - A) + (14 - Bq) with A = sum u_e, Bq = sum (e/2) u_e: two instructions per
+      // node instead of three (jb = j/2 of the pair's first node)
+      float A = 0.f, Bq = 0.f;
 #pragma unroll
       for (int e = 7; e >= 0; --e) {
         un = fmaf(-cv[e], un, dv[e]);
         ov[e] = un;
-        Mh = fmaf(jb + 0.5f * e, 1.f - un, Mh);
+        A += un;
+        Bq = fmaf(0.5f * e, un, Bq);
         umin = fminf(umin, un);
       }
+      Mh += fmaf(2.f * (float)(c - 1), 8.f - A, 14.f - Bq);
       sts4(a1, ov[4], ov[5], ov[6], ov[7]);
       sts4(a0, ov[0], ov[1], ov[2], ov[3]);
     }
@@ -612,18 +616,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
     // ------------------------------------------------------------------ warp-private tile pipeline
     RotorAcc<TC> acc;
     acc.clear();
+    LaneLoc Ln;
+    Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
+    if (warp < ntiles) Ln = locate(sh, warp, lane, T, P, ntot);
     for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
-      const LaneLoc Lc = locate(sh, tile, lane, T, P, ntot);
+      const LaneLoc Lc = Ln;
       const Seg sg = segments(Lc, lane);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)sg.nvalid * WG_ROW_BYTES);
       __syncwarp();
-      const size_t st_c = (size_t)Lc.chain * P + Lc.slot;
-      if (sg.start) bulk_g2s(row_a, prof + st_c * WG_NR, (uint32_t)sg.len * WG_ROW_BYTES, bar);
+      const unsigned st_c = (unsigned)(Lc.chain * P + Lc.slot);  // < T * P: 32-bit offsets inside the farm's block
+      if (sg.start) bulk_g2s(row_a, prof + st_c * (unsigned)WG_NR, (uint32_t)sg.len * WG_ROW_BYTES, bar);
       // station scalars: in flight together with the tile, consumed after the mbarrier wait
       float4 pmc = make_float4(0.f, 0.f, 0.f, 0.f), pcc = pmc;
       if (Lc.valid) {
-        pmc = __ldcg(reinterpret_cast<const float4*>(pm_old + st_c * 4));
-        pcc = __ldcg(reinterpret_cast<const float4*>(pcon + st_c * 4));
+        pmc = __ldcg(reinterpret_cast<const float4*>(pm_old + st_c * 4u));
+        pcc = __ldcg(reinterpret_cast<const float4*>(pcon + st_c * 4u));
       }
       // age neighbours outside this tile (older = flat index - 1 of the same chain, younger = + 1): pull their
       // scalars towards L2 now, they are loaded after the march
@@ -635,18 +642,19 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
       const bool need_y = has_y && (lane == 31 || !vy_ || ch_y != Lc.chain);
       if (need_o || need_y) {
         const int sx = need_o ? (Lc.slot == 0 ? P - 1 : Lc.slot - 1) : (Lc.slot == P - 1 ? 0 : Lc.slot + 1);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + ((size_t)Lc.chain * P + sx) * 4));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + ((size_t)Lc.chain * P + sx) * 4));
+        const unsigned st_x = (unsigned)(Lc.chain * P + sx);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st_x * 4u));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st_x * 4u));
       }
-      // while the tile is in flight: pull the next tile's rows and scalars towards L2
+      // while the tile is in flight: find the next tile and pull its rows and scalars towards L2
       if (tile + WG_NWARP < ntiles) {
-        const LaneLoc Ln = locate(sh, tile + WG_NWARP, lane, T, P, ntot);
+        Ln = locate(sh, tile + WG_NWARP, lane, T, P, ntot);
         if (Ln.valid) {
-          const size_t st = (size_t)Ln.chain * P + Ln.slot;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + st * WG_NR));
+          const unsigned st = (unsigned)(Ln.chain * P + Ln.slot);
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + st * (unsigned)WG_NR));
           if (lane == 0 || (Ln.slot & 7) == 0) {  // the station scalars: one 128-byte line per 8 slots
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st * 4));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st * 4));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st * 4u));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st * 4u));
           }
         }
       }
@@ -662,12 +670,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
         const float ucn = march_row_tmem(rowk, taddr, dx * rR, xt_mid, pcc.y);
-        if (Lc.valid) *reinterpret_cast<float4*>(pm_new + st_c * 4) = make_float4(xn, yn, zn, ucn);
+        if (Lc.valid) *reinterpret_cast<float4*>(pm_new + st_c * 4u) = make_float4(xn, yn, zn, ucn);
       }
       fence_async_smem();
       __syncwarp();
       if (sg.start) {  // write the marched rows back (same segments as the load)
-        bulk_s2g(prof + st_c * WG_NR, row_a, (uint32_t)sg.len * WG_ROW_BYTES);
+        bulk_s2g(prof + st_c * (unsigned)WG_NR, row_a, (uint32_t)sg.len * WG_ROW_BYTES);
         bulk_commit();
       }
       // ---- superposition: which rotor planes does this station bracket together with its age neighbours?
@@ -675,17 +683,17 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
         if (need_o) {
-          const size_t sx = (size_t)Lc.chain * P + (Lc.slot == 0 ? P - 1 : Lc.slot - 1);
-          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4));
-          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4));
+          const unsigned sx = (unsigned)(Lc.chain * P + (Lc.slot == 0 ? P - 1 : Lc.slot - 1));
+          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
+          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4u));
           const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
           moved(pm, pc, ws, dt, tvx, xo, yo, zo, dxx);
         }
         if (need_y) {
-          const size_t sx = (size_t)Lc.chain * P + (Lc.slot == P - 1 ? 0 : Lc.slot + 1);
-          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4));
-          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4));
+          const unsigned sx = (unsigned)(Lc.chain * P + (Lc.slot == P - 1 ? 0 : Lc.slot + 1));
+          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
+          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4u));
           const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
           moved(pm, pc, ws, dt, tvx, xy, yy, zy, dxx);
@@ -712,40 +720,37 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
         if (nmax > 0) {
           const float rdA = rcp_fast(xo - xn), rdB = rcp_fast(xn - xy);
           for (int it = 0; it < nmax; ++it) {
-            {  // interval A hits of this pass
-              const int kA = a_lo + it;
-              const int jA = it < nA ? sh.ord[kA] : Lc.chain;
-              const bool hitA = jA != Lc.chain;
-              const unsigned mA = __ballot_sync(full, hitA);
-              if (hitA) {
-                const float w = (sh.xs[kA] - xn) * rdA;
-                const float wg = kA >= cn ? 1.f - w : w - 1.f;
-                const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
-                const int p = __popc(mA & lt);
-                ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
-                hb[p] = rowk | ((uint32_t)jA << 20);
-              }
+            const int kA = a_lo + it, kB = b_lo + it;
+            const int jA = it < nA ? sh.ord[kA] : Lc.chain, jB = it < nB ? sh.ord[kB] : Lc.chain;
+            const bool hitA = jA != Lc.chain, hitB = jB != Lc.chain;
+            const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
+            const int nhA = __popc(mA), nhB = __popc(mB);
+            const bool split = nhA + nhB > WG_HIT_CAP;  // rare: evaluate the two interval kinds one after the other
+            if (hitA) {
+              const float w = (sh.xs[kA] - xn) * rdA;
+              const float wg = kA >= cn ? 1.f - w : w - 1.f;
+              const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
+              const int p = __popc(mA & lt);
+              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
+              hb[p] = rowk | ((uint32_t)jA << 20);
+            }
+            if (split) {
               __syncwarp();
-              if (mA) flush_hits<TC>(ha, hb, __popc(mA), acc, lane, qy, qz);
+              flush_hits<TC>(ha, hb, nhA, acc, lane, qy, qz);
               __syncwarp();
             }
-            {  // interval B hits of this pass
-              const int kB = b_lo + it;
-              const int jB = it < nB ? sh.ord[kB] : Lc.chain;
-              const bool hitB = jB != Lc.chain;
-              const unsigned mB = __ballot_sync(full, hitB);
-              if (hitB) {
-                const float w = (sh.xs[kB] - xy) * rdB;
-                const float wg = kB >= cy ? w : -w;
-                const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
-                const int p = __popc(mB & lt);
-                ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
-                hb[p] = rowk | ((uint32_t)jB << 20);
-              }
-              __syncwarp();
-              if (mB) flush_hits<TC>(ha, hb, __popc(mB), acc, lane, qy, qz);
-              __syncwarp();
+            if (hitB) {
+              const float w = (sh.xs[kB] - xy) * rdB;
+              const float wg = kB >= cy ? w : -w;
+              const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
+              const int p = (split ? 0 : nhA) + __popc(mB & lt);
+              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
+              hb[p] = rowk | ((uint32_t)jB << 20);
             }
+            const int nh = split ? nhB : nhA + nhB;
+            __syncwarp();
+            if (nh > 0) flush_hits<TC>(ha, hb, nh, acc, lane, qy, qz);
+            __syncwarp();
           }
         }
       }
