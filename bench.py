@@ -322,6 +322,34 @@ def run_gpu(a):
     t_flow = flow_ms / max(n_prof, 1) * 1e-3
     env.check_flags()
 
+    # ---- SURVEY 8(d) metric (ii): throughput WITH auto-reset (episodes of the reference's length, n_passthrough = 5,
+    # envs at random phases of their episodes, finished envs replaced from the spare pool, spin-up in the background)
+    auto = None
+    if not a.no_autoreset:
+        from windgym_b200 import PooledVecEnv
+        from windgym_b200.vector import GymVectorEnv
+        env.close(); del env
+        torch.cuda.empty_cache()
+        K_ar = max(K, 200)
+        pool = PooledVecEnv(V80(), B, reserve=max(64, B // 8), config=cfg, device=str(dev), n_passthrough=5, seed=rank, **kw)
+        genv = GymVectorEnv(venv=pool, as_torch=True)
+        genv.reset(seed=rank)
+        prng = np.random.default_rng(rank)
+        pool.state["timestep"][:] = torch.as_tensor((prng.uniform(0, 1, B) * pool.time_max).astype(np.int32), device=dev)
+        for i in range(10):
+            genv.step(acts_dev[i % (W + K)])
+        barrier()
+        n_res = 0
+        t0 = time.perf_counter()
+        for i in range(K_ar):
+            _, _, _, tr_ar, _ = genv.step(acts_dev[i % (W + K)])
+            n_res += int(tr_ar.sum())
+        torch.cuda.synchronize()
+        t_ar = (time.perf_counter() - t0) * 1e3
+        pool.check_flags()
+        auto = {"ms": t_ar, "steps": K_ar, "resets": n_res, "stats": dict(pool.stats), "reserve": pool.reserve}
+        pool.close()
+
     # ---- max over ranks
     tt = torch.tensor([t_ms, t_e2e_ms, t_flow * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -351,6 +379,14 @@ def run_gpu(a):
                          "algorithmic_bytes_per_launch": bytes_flow, "launches_timed": int(n_prof)},
             "clocks": clk,
         }
+        if auto is not None:   # rank 0's share, whole-job value extrapolated over the ranks (no cross-rank coupling)
+            line["with_autoreset"] = {
+                "value": world * B * auto["steps"] / (auto["ms"] * 1e-3), "unit": UNIT, "ms_per_step": auto["ms"] / auto["steps"],
+                "steps": auto["steps"], "episodes_finished": auto["resets"], "spare_envs": auto["reserve"],
+                "pool": auto["stats"],
+                "what": "steady-state training loop: n_passthrough=5 episodes at random phases, finished envs swapped for "
+                        "pre-developed spares (spin-up batched on a background stream), truncation flags read on the host "
+                        "every step (wall clock)"}
         line["config"]["n_passthrough"] = n_pass
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_port_single(a.nx, a.ny, a.reward)
@@ -373,6 +409,7 @@ def main():
     ap.add_argument("--reward", default="Power_avg", choices=["Power_avg", "Baseline"],
                     help="Baseline adds the second (greedy-controller) farm per env: 2x the flow work")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-autoreset", action="store_true", help="skip the with_autoreset leg")
     ap.add_argument("--turbtype", default="None", choices=["None", "Mann"],
                     help="Mann: ambient Mann turbulence box (meandering + rotor fluctuations); not the headline config")
     a = ap.parse_args()

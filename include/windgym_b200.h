@@ -133,6 +133,15 @@ int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream)
 int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float* wd, const float* yaw,
                         const float* power, float* obs, void* cuda_stream);
 
+/* Auto-reset without a stall (the reference resets inside step(): Wind_Farm_Env.py:1003-1025 tears the episode
+ * down, callers such as SB3's VecEnv reset immediately; reset = t_developed + fill flow steps, :722-766).
+ * wg_set_active: wg_step advances only the first n_active envs of the allocation; the remaining slots are a pool
+ * of spare envs the caller spins up in the background (wg_reset with a mask, on another stream).
+ * wg_copy_envs: copy the complete per-env state of slot src[k] into slot dst[k] (src, dst: device int32 [n]) --
+ * swap a pre-developed spare env in for an env whose episode just ended. */
+int wg_set_active(wg_handle* h, int32_t n_active);
+int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* dst, int32_t n, void* cuda_stream);
+
 /* TurbulenceFieldSite over a MannTurbulenceField (_def_site, Wind_Farm_Env.py:598-678): attach one periodic
  * turbulence box, shared read-only by every env of the handle, in the two layouts the flow kernel samples:
  * raw_uvw0 device [nx,ny,nz,4] f32 (u, v, w, 0) and lp_vw device [nx,ny,nz,2] f32 ((v, w) low-pass filtered in

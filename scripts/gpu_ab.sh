@@ -9,7 +9,7 @@ fi
 i=0
 for S in $SETTINGS; do
   i=$((i+1))
-  env $(echo $S | tr ',' ' ') timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu > gpurun_out/${TAG}_bench_$i.json 2> gpurun_out/${TAG}_bench_$i.err
+  env $(echo $S | tr ',' ' ') timeout 600 python bench.py --steps 100 --warmup 10 --no-cpu --no-autoreset > gpurun_out/${TAG}_bench_$i.json 2> gpurun_out/${TAG}_bench_$i.err
   python - <<PY
 import json
 try:

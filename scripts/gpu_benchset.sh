@@ -4,7 +4,7 @@ TAG=${1:-set}
 mkdir -p gpurun_out
 run() { # name args...
   local name=$1; shift
-  timeout 900 python bench.py --steps 60 --warmup 6 --no-cpu "$@" > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+  timeout 900 python bench.py --steps 60 --warmup 6 --no-cpu --no-autoreset "$@" > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
   python - <<PY
 import json
 try:

@@ -12,12 +12,12 @@ if [ -z "$2" ]; then
 fi
 timeout 600 python bench.py --steps 100 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
-timeout 600 python bench.py --steps 60 --warmup 5 --reward Baseline --no-cpu > gpurun_out/${TAG}_bench_baseline.json 2>> gpurun_out/${TAG}_bench.err
+timeout 600 python bench.py --steps 60 --warmup 5 --reward Baseline --no-cpu --no-autoreset > gpurun_out/${TAG}_bench_baseline.json 2>> gpurun_out/${TAG}_bench.err
 cat gpurun_out/${TAG}_bench_baseline.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
-  --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 8 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_launch.log 2>&1
+  --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 8 --warmup 3 --no-cpu --no-autoreset > gpurun_out/${TAG}_ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:wg_flow_kernel -s 30 -c 2 \
-  -f -o gpurun_out/${TAG}_flow python bench.py --steps 8 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+  -f -o gpurun_out/${TAG}_flow python bench.py --steps 8 --warmup 3 --no-cpu --no-autoreset > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la gpurun_out

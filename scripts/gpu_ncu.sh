@@ -2,5 +2,5 @@
 TAG=$1; shift
 export "$@"
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:wg_flow_kernel -s 30 -c 1 -f -o gpurun_out/${TAG}_flow python bench.py --steps 8 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:wg_flow_kernel -s 30 -c 1 -f -o gpurun_out/${TAG}_flow python bench.py --steps 8 --warmup 3 --no-cpu --no-autoreset > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"

@@ -146,3 +146,45 @@ def test_flow_field_and_render_vs_oracle(built_lib):
     assert img.shape == (250, 250, 3) and img.dtype == np.uint8 and len(np.unique(img.reshape(-1, 3), axis=0)) > 20
     assert (img.reshape(-1, 3).sum(1) == 0).sum() >= 4 * 20               # rotors drawn
     env.close()
+
+
+def test_pooled_autoreset_swaps_in_predeveloped_envs(built_lib):
+    """Auto-reset through the spare pool: a swapped-in env is exactly a freshly reset env on its conditions, the
+    pool recycles, and a dry pool falls back to the synchronous masked reset."""
+    import torch
+    from windgym_b200 import GymVectorEnv, PooledVecEnv, V80, VecWindFarmEnv
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    B, T = 6, 2
+    pool = PooledVecEnv(V80(), B, reserve=4, refill_chunk=2, config=cfg, n_passthrough=0.2, seed=9, device="cuda:0")
+    env = GymVectorEnv(venv=pool)
+    obs, infos = env.reset(seed=9)
+    assert obs.shape == (B, 4) and pool.state["yaw"].shape[0] == B and pool.inner.state["yaw"].shape[0] == B + 4
+    checked = 0
+    for k in range(60):
+        ws_before = pool.ws.copy()
+        obs, r, term, trunc, infos = env.step(np.zeros((B, T), dtype=np.float32))
+        assert obs.shape == (B, 4) and np.isfinite(obs).all() and infos["Power agent"].shape == (B,)
+        if trunc.any():
+            ts = pool.state["timestep"].cpu().numpy()
+            assert (ts[trunc] == 0).all()
+            assert (pool.ws[trunc] != ws_before[trunc]).all() and (pool.ws[~trunc] == ws_before[~trunc]).all()
+            if checked < 3:   # the swapped-in state is a genuine reset onto the env's (new) conditions
+                fresh = VecWindFarmEnv(V80(), B, config=cfg, n_passthrough=0.2, device="cuda:0")
+                f_obs, _ = fresh.reset(wind=(pool.ws, pool.ti, pool.wd), yaw0=pool.state["yaw"][:, 0].cpu().numpy())
+                assert np.array_equal(f_obs.cpu().numpy()[trunc], obs[trunc])
+                for key in ("count", "head", "n_step", "power"):
+                    a, b = fresh.state[key].cpu().numpy(), pool.state[key].cpu().numpy()
+                    assert np.array_equal(a[trunc], b[trunc]), key
+                assert np.array_equal(fresh.time_max[trunc], pool.time_max[trunc])
+                fresh.close()
+                checked += 1
+    pool.check_flags()
+    assert checked == 3 and pool.stats["swapped"] >= 10 and pool.stats["refills"] >= 3
+    pool.close()
+    # a pool of one spare runs dry when several envs finish together: the rest is reset synchronously
+    tiny = PooledVecEnv(V80(), 4, reserve=1, config=cfg, n_passthrough=0.2, seed=1, device="cuda:0")
+    tiny.reset(seed=1)
+    tiny.reset(mask=np.array([True, True, True, False]))
+    assert tiny.stats["swapped"] == 1 and tiny.stats["sync_resets"] == 2
+    assert (tiny.state["timestep"].cpu().numpy() == 0).all() and np.isfinite(tiny.obs.cpu().numpy()).all()
+    tiny.close()

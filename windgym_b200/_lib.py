@@ -65,6 +65,8 @@ SYMBOLS = {
     "wg_flow_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_mes_push_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "wg_set_active": (C.c_int, [C.c_void_p, C.c_int32]),
+    "wg_copy_envs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_set_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_float]),
     "wg_flow_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

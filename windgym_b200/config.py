@@ -132,6 +132,7 @@ class EnvConfig:
     # per-env quantities the reference computes at reset (Wind_Farm_Env.py:723-732), in fp64
     def reset_integers(self, ws, wd):
         ws = np.asarray(ws, dtype=np.float64)
+        ws = np.where(ws > 0, ws, 1.0)   # slots that were never reset (spare pool) carry no conditions yet
         xr, _ = rotate_layout(self.x_pos, self.y_pos, wd)
         dist = xr.max(axis=-1) - xr.min(axis=-1)
         t_inflow = dist / ws

@@ -45,6 +45,9 @@ struct wg_handle {
   double *d_x = nullptr, *d_y = nullptr;
   int *d_ring_off = nullptr, *d_ring_chan = nullptr;
   wg::ObsDesc* d_desc = nullptr;
+  wg::CopyField* d_copy = nullptr;
+  int n_copy = 0;
+  int n_active = 0;  // envs stepped by wg_step (prefix of the allocation; the rest is the spare pool)
 };
 
 namespace {
@@ -267,7 +270,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
 
   wg::Dev& d = h->dev;
   memset(&d, 0, sizeof(d));
-  d.B = B; d.T = T; d.F = F; d.P = P; d.S = cfg->substeps; d.n_tab = cfg->n_tab;
+  d.B = B; d.Bg = B; d.T = T; d.F = F; d.P = P; d.S = cfg->substeps; d.n_tab = cfg->n_tab;
+  h->n_active = B;
   d.dt = cfg->dt; d.D = cfg->diameter; d.R = 0.5f * cfg->diameter; d.zh = cfg->hub_height; d.d_particle = cfg->d_particle;
   d.yaw_min = cfg->yaw_min; d.yaw_max = cfg->yaw_max; d.yaw_step = cfg->yaw_step;
   d.action_method = cfg->action_method; d.base_controller = cfg->base_controller;
@@ -307,6 +311,22 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "farm_pow_ring", 0, {B, cfg->power_avg});
   add_field(h, "base_pow_ring", 0, {B, cfg->power_avg});
   h->state_bytes = (h->state_bytes + 255) / 256 * 256;
+  // field table of the env-copy kernel: leading dimension B, or [2, B, ...] for the ping-pong buffer
+  std::vector<wg::CopyField> cf;
+  for (auto& f : h->fields) {
+    size_t total = 4;
+    for (auto sdim : f.shape) total *= (size_t)sdim;
+    wg::CopyField c{};
+    c.offset = f.offset;
+    if (f.shape[0] == B) { c.n_rep = 1; c.rep_stride = 0; c.per_env = (unsigned)(total / B); }
+    else { c.n_rep = (unsigned)f.shape[0]; c.rep_stride = total / f.shape[0]; c.per_env = (unsigned)(total / f.shape[0] / B); }
+    cf.push_back(c);
+  }
+  h->n_copy = (int)cf.size();
+  if ((e = upload(&h->d_copy, cf.data(), cf.size())) != cudaSuccess) {
+    wg_destroy(h);
+    return cuda_fail(e, "wg_create upload");
+  }
   *out = h;
   return WG_OK;
 }
@@ -315,7 +335,7 @@ void wg_destroy(wg_handle* h) {
   if (!h) return;
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   cudaFree(h->d_tab_ws); cudaFree(h->d_tab_p); cudaFree(h->d_tab_ct); cudaFree(h->d_x); cudaFree(h->d_y);
-  cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc);
+  cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc); cudaFree(h->d_copy);
   delete h;
 }
 
@@ -409,6 +429,7 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   if (!h || !state || !actions || !obs || !reward || !truncated) return fail(WG_ERR_INVALID, "wg_step: null argument");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   wg::Dev d = bind(h, state);
+  d.Bg = h->n_active;
   cudaEvent_t* ev = nullptr;
   if (h->profiling) {
     if (h->prof_used + 3 > h->prof_events.size()) {
@@ -453,6 +474,23 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   d.tb_n[0] = nx; d.tb_n[1] = ny; d.tb_n[2] = nz;
   d.tb_inv_d[0] = 1.f / dx; d.tb_inv_d[1] = 1.f / dy; d.tb_inv_d[2] = 1.f / dz;
   d.tb_len_x = (float)((double)nx * (double)dx);
+  return WG_OK;
+}
+
+int wg_set_active(wg_handle* h, int32_t n_active) {
+  if (!h) return fail(WG_ERR_INVALID, "wg_set_active: null argument");
+  if (n_active < 1 || n_active > h->cfg.n_envs) return fail(WG_ERR_INVALID, "n_active must be in 1..n_envs");
+  h->n_active = n_active;
+  return WG_OK;
+}
+
+int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* dst, int32_t n, void* cuda_stream) {
+  if (!h || !state || !src || !dst) return fail(WG_ERR_INVALID, "wg_copy_envs: null argument");
+  if (n < 0) return fail(WG_ERR_INVALID, "n must be >= 0");
+  if (n == 0) return WG_OK;
+  WG_LAUNCH(wg::launch_copy_envs(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, src, dst, n,
+                                 (cudaStream_t)cuda_stream),
+            "wg_copy_envs_kernel");
   return WG_OK;
 }
 

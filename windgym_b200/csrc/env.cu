@@ -82,7 +82,7 @@ template <bool STAGE>
 __global__ void __launch_bounds__(WG_FIN_WARPS * 32) wg_finish_kernel(const Dev d, const FinishArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
   const int b = blockIdx.x * WG_FIN_WARPS + warp;
-  if (b >= d.B) return;
+  if (b >= d.Bg) return;
   if (a.mask && !a.mask[b]) return;
   extern __shared__ float s_dyn[];
   __shared__ float s_vals[WG_FIN_WARPS][4][WG_MAX_T];
@@ -284,7 +284,7 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
 
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(float) * WG_FIN_WARPS * ((size_t)d.ring_floats + 2 * (size_t)d.power_avg);
-  const int grid = (d.B + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
+  const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
   if (smem <= 100 * 1024) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
@@ -301,6 +301,37 @@ cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
 
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s) {
   wg_reset_init_kernel<<<d.B, 64, 0, s>>>(d, a);
+  return cudaGetLastError();
+}
+
+// Copy every per-env field of slot src[k] to slot dst[k] (swap-in of a pre-developed spare env on auto-reset).
+__global__ void __launch_bounds__(256) wg_copy_envs_kernel(unsigned char* __restrict__ state,
+                                                           const CopyField* __restrict__ fields, const int* __restrict__ src,
+                                                           const int* __restrict__ dst, int n) {
+  const CopyField f = fields[blockIdx.y];
+  const int k = blockIdx.z;
+  if (k >= n) return;
+  const size_t so = (size_t)src[k] * f.per_env, dof = (size_t)dst[k] * f.per_env;
+  for (unsigned r = 0; r < f.n_rep; ++r) {
+    unsigned char* base = state + f.offset + (size_t)r * f.rep_stride;
+    if ((f.per_env & 15u) == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(base + so);
+      uint4* d4 = reinterpret_cast<uint4*>(base + dof);
+      for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < f.per_env / 16; i += gridDim.x * blockDim.x) d4[i] = s4[i];
+    } else {
+      const unsigned* s1 = reinterpret_cast<const unsigned*>(base + so);
+      unsigned* d1 = reinterpret_cast<unsigned*>(base + dof);
+      for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < f.per_env / 4; i += gridDim.x * blockDim.x) d1[i] = s1[i];
+    }
+  }
+}
+
+cudaError_t launch_copy_envs(unsigned char* state, const CopyField* fields, int n_fields, const int* src, const int* dst,
+                             int n, cudaStream_t s) {
+  for (int k0 = 0; k0 < n; k0 += 65535) {
+    const int nk = n - k0 < 65535 ? n - k0 : 65535;
+    wg_copy_envs_kernel<<<dim3(24, n_fields, nk), 256, 0, s>>>(state, fields, src + k0, dst + k0, nk);
+  }
   return cudaGetLastError();
 }
 

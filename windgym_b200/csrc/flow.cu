@@ -905,7 +905,7 @@ static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  wg_flow_kernel<TC, TURB><<<d.B * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  wg_flow_kernel<TC, TURB><<<d.Bg * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
 

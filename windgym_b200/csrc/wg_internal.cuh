@@ -43,6 +43,7 @@ struct ObsDesc {
 struct Dev {
   // dims
   int B, T, F, P, S, n_tab;
+  int Bg;  // envs [0, Bg) are launched: the whole allocation B, or the active prefix for wg_step (wg_set_active)
   float dt, D, R, zh, d_particle;
   float yaw_min, yaw_max, yaw_step;
   int action_method, base_controller;
@@ -178,6 +179,13 @@ void set_rotor_points(const float* qy, const float* qz);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
+// one state field as the env-copy kernel sees it: n_rep blocks of B envs, per_env bytes each
+struct CopyField {
+  unsigned long long offset, rep_stride;
+  unsigned per_env, n_rep;
+};
+cudaError_t launch_copy_envs(unsigned char* state, const CopyField* fields, int n_fields, const int* src, const int* dst,
+                             int n, cudaStream_t s);
 cudaError_t launch_flow_field(const Dev& d, int b, int f, const float* px, const float* py, int n, float z, float* out,
                               cudaStream_t s);
 

@@ -303,12 +303,31 @@ class VecWindFarmEnv:
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
         actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        if actions.numel() != self.n_envs * self.n_turb:
-            raise ValueError(f"actions must have {self.n_envs}x{self.n_turb} elements")
+        n_act = getattr(self, "n_active", self.n_envs)
+        if actions.numel() != n_act * self.n_turb:
+            raise ValueError(f"actions must have {n_act}x{self.n_turb} elements")
         _lib.check(self.lib.wg_step(self._h, _ptr(self._state), _ptr(actions), _ptr(self.obs), _ptr(self.reward),
                                     _ptr(self.truncated), self._stream()))
         self._last_actions = actions
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
+
+    def set_active(self, n_active):
+        """``wg_set_active``: ``step()`` advances only envs [0, n_active); the other slots are a spare pool
+        (``windgym_b200.pool.PooledVecEnv``)."""
+        _lib.check(self.lib.wg_set_active(self._h, int(n_active)))
+        self.n_active = int(n_active)
+
+    def copy_envs(self, src, dst):
+        """``wg_copy_envs``: complete per-env state of slot src[k] -> slot dst[k] (device copy on the current stream)."""
+        s = torch.as_tensor(np.asarray(src, dtype=np.int32)).to(self.device)
+        t = torch.as_tensor(np.asarray(dst, dtype=np.int32)).to(self.device)
+        _lib.check(self.lib.wg_copy_envs(self._h, _ptr(self._state), _ptr(s), _ptr(t), int(s.numel()), self._stream()))
+        self._keep_copy = (s, t)
+        self.obs[t.long()] = self.obs[s.long()]
+        for arr in (self.ws, self.ti, self.wd, self.time_max):
+            arr[np.asarray(dst)] = arr[np.asarray(src)]
+        if getattr(self, "turb_box", None) is not None:
+            self.turb_offset[np.asarray(dst)] = self.turb_offset[np.asarray(src)]
 
     def flow_steps(self, n):
         """DWMFlowSimulation.run(n*dt) for every env and farm, without measurement bookkeeping."""
