@@ -85,7 +85,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE,
+                                       "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE,
                                       stderr=subprocess.DEVNULL, text=True)
         except OSError:
             pass

@@ -682,15 +682,17 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
       {
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        if (need_o) {
-          const unsigned sx = (unsigned)(Lc.chain * P + (Lc.slot == 0 ? P - 1 : Lc.slot - 1));
+        if (need_o || need_y) {  // one out-of-tile neighbour per lane (the older one if it needs both)
+          const unsigned sx = (unsigned)(Lc.chain * P + (need_o ? (Lc.slot == 0 ? P - 1 : Lc.slot - 1)
+                                                                : (Lc.slot == P - 1 ? 0 : Lc.slot + 1)));
           const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
           const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4u));
           const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
           float dxx;
-          moved(pm, pc, ws, dt, tvx, xo, yo, zo, dxx);
+          if (need_o) moved(pm, pc, ws, dt, tvx, xo, yo, zo, dxx);
+          else moved(pm, pc, ws, dt, tvx, xy, yy, zy, dxx);
         }
-        if (need_y) {
+        if (need_o && need_y) {  // rare: a one-station segment needs both neighbours from outside the tile
           const unsigned sx = (unsigned)(Lc.chain * P + (Lc.slot == P - 1 ? 0 : Lc.slot + 1));
           const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
           const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4u));

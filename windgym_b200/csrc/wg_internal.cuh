@@ -84,7 +84,7 @@ struct Dev {
   const float4* tb_raw;   // [Nx,Ny,Nz] (u, v, w, 0)
   const float2* tb_lp;    // [Nx,Ny,Nz] (v, w) low-pass filtered in y, z: moves the wake centres
   int tb_n[3];
-  float tb_inv_d[3], tb_len_x;
+  float tb_inv_d[3], tb_inv_n[3], tb_len_x;
   float *tb_off;          // [B,3] position of the env inside the box [m]
   float *tb_scale;        // [B]   scale_TI factor
 };
@@ -118,17 +118,19 @@ struct BoxIdx {
   int i[2], j[2], k[2];
   float fx, fy, fz;
 };
-__device__ __forceinline__ int wrap_cell(float fl, int n) {
-  int i = (int)fl % n;
-  return i < 0 ? i + n : i;
+// cell index and fraction of a periodic coordinate without integer division: X - n floor(X / n), then floor
+__device__ __forceinline__ void wrap_cell(float X, int n, float inv_n, int& i0, int& i1, float& fr) {
+  const float Xw = fmaf(-(float)n, floorf(X * inv_n), X);
+  const float f0 = floorf(Xw);
+  fr = Xw - f0;
+  i0 = min(max((int)f0, 0), n - 1);  // rounding at the seam can land on -0 / n
+  i1 = i0 + 1 == n ? 0 : i0 + 1;
 }
 __device__ __forceinline__ BoxIdx box_index(const Dev& d, float X, float Y, float Z) {
   BoxIdx b;
-  const float x0 = floorf(X), y0 = floorf(Y), z0 = floorf(Z);
-  b.fx = X - x0; b.fy = Y - y0; b.fz = Z - z0;
-  b.i[0] = wrap_cell(x0, d.tb_n[0]); b.i[1] = b.i[0] + 1 == d.tb_n[0] ? 0 : b.i[0] + 1;
-  b.j[0] = wrap_cell(y0, d.tb_n[1]); b.j[1] = b.j[0] + 1 == d.tb_n[1] ? 0 : b.j[0] + 1;
-  b.k[0] = wrap_cell(z0, d.tb_n[2]); b.k[1] = b.k[0] + 1 == d.tb_n[2] ? 0 : b.k[0] + 1;
+  wrap_cell(X, d.tb_n[0], d.tb_inv_n[0], b.i[0], b.i[1], b.fx);
+  wrap_cell(Y, d.tb_n[1], d.tb_inv_n[1], b.j[0], b.j[1], b.fy);
+  wrap_cell(Z, d.tb_n[2], d.tb_inv_n[2], b.k[0], b.k[1], b.fz);
   return b;
 }
 // low-pass (v, w) at a wake centre; xs = Taylor shift U t - x_off (so that the box x is x - xs)
@@ -139,14 +141,17 @@ __device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, floa
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
+    for (int bb = 0; bb < 2; ++bb) {
+      const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
+      const float2* rowp = d.tb_lp + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float wt = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy) * (c ? b.fz : 1.f - b.fz);
-        const float2 q = __ldg(d.tb_lp + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2] + b.k[c]);
+        const float wt = wxy * (c ? b.fz : 1.f - b.fz);
+        const float2 q = __ldg(rowp + b.k[c]);
         v = fmaf(wt, q.x, v);
         w = fmaf(wt, q.y, w);
       }
+    }
   return make_float2(v * scale, w * scale);
 }
 __device__ __forceinline__ float4 sample_raw(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
@@ -156,15 +161,18 @@ __device__ __forceinline__ float4 sample_raw(const Dev& d, float x, float y, flo
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int bb = 0; bb < 2; ++bb)
+    for (int bb = 0; bb < 2; ++bb) {
+      const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
+      const float4* rowp = d.tb_raw + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        const float wt = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy) * (c ? b.fz : 1.f - b.fz);
-        const float4 q = __ldg(d.tb_raw + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2] + b.k[c]);
+        const float wt = wxy * (c ? b.fz : 1.f - b.fz);
+        const float4 q = __ldg(rowp + b.k[c]);
         u = fmaf(wt, q.x, u);
         v = fmaf(wt, q.y, v);
         w = fmaf(wt, q.z, w);
       }
+    }
   return make_float4(u * scale, v * scale, w * scale, 0.f);
 }
 // Taylor shift of the box at flow time t = n dt, reduced modulo the box length in double so that the float
