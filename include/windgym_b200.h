@@ -150,6 +150,13 @@ int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* d
 int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, int32_t nx, int32_t ny, int32_t nz,
                       float dx, float dy, float dz);
 
+/* addedTurbulenceModel = SynchronizedAutoScalingIsotropicMannTurbulence() (Wind_Farm_Env.py:618,:639,:658): a
+ * unit-variance isotropic box iso_uvw0 (device [nx,ny,nz,4] f32), advected with the ambient box; inside wakes the
+ * rotor inflow gains k_mt(r) * U0 * iso with k_mt = k_m1 |1 - U(r)| + k_m2 |dU/dr| (Madsen et al. 2010).  Needs
+ * wg_set_turbulence first; NULL switches it off. */
+int wg_set_added_turbulence(wg_handle* h, const float* iso_uvw0, int32_t nx, int32_t ny, int32_t nz, float dx, float dy,
+                            float dz, float k_m1, float k_m2);
+
 /* DWMFlowSimulation.get_windspeed(view, include_wakes=True) (render path, Wind_Farm_Env.py:1056; view :470-476):
  * wake-superposed (u, v, w) of farm `farm` of env `env` at n_points points (x[i], y[i], z) of the wind-aligned
  * frame of positions_xyz.  x, y: device [n_points]; out_uvw: device [3, n_points]. */

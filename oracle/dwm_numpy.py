@@ -17,7 +17,8 @@ inflow U0e):
   ``turbtype="None"`` path, ``Wind_Farm_Env.py:661-665``), or (ws, 0, 0) + a frozen Mann box advected with ws
   (``oracle/mann_numpy.py``; ``MannLoad`` / ``MannGenerate`` / ``MannFixed``, ``Wind_Farm_Env.py:612-659``): the
   low-pass filtered (v', w') at a particle's centre move it (meandering, Larsen et al. 2008), the raw box averaged
-  over the rotor's quadrature points is added to the rotor inflow.  Added wake turbulence is not restated.
+  over the rotor's quadrature points is added to the rotor inflow.  Wake-added turbulence (Madsen et al. 2010):
+  inside wakes the rotor points gain w U0e k_mt(r) times a unit-variance isotropic box, k_mt = 0.6 |1-U| + 0.35 |dU/dr|.
 * Turbine: tabular P/CT, py_wake ``SimpleYawModel``: P = P_tab(u cos g), CT = CT_tab(u cos g) cos^2 g,
   induction a = (1 - sqrt(1 - CT)) / 2.
 * Wake particles (Larsen et al. 2008, Wind Energy 11:377): one chain per turbine; a particle is released at
@@ -50,6 +51,8 @@ CT_MAX = 0.96
 MARGIN_D = 2.0
 N_Q = 16
 DXT_MIN = 1e-6
+K_M1 = 0.6    # wake-added turbulence, Madsen et al. (2010) / IEC 61400-1 ed.4 Annex E: k_mt = k_m1 |1-U| + k_m2 |dU/dr|
+K_M2 = 0.35
 
 
 def rotor_points():
@@ -142,6 +145,14 @@ def ainslie_march(U, dxt, xt, knu1):
     for j in range(N_R - 3, -1, -1):
         Un[:, j] = dp[:, j] - cp[:, j] * Un[:, j + 1]
     return Un, nu
+
+
+def profile_gradient_at(U, r):
+    """|dU/dr| (per rotor radius) of the cell that holds r: the slope of the linear interpolant; zero beyond the grid."""
+    s = r / DR
+    j0 = np.minimum(np.floor(s).astype(np.int64), N_R - 2)
+    rows = np.arange(U.shape[0])[:, None]
+    return np.where(s >= N_R - 1, 0.0, np.abs(U[rows, j0 + 1] - U[rows, j0]) / DR)
 
 
 def profile_deficit_at(U, r):
@@ -302,6 +313,9 @@ class DWMFlowSimulation:
         self.last_nu = None
         tf = getattr(site, "turbulenceField", None)
         self.tf = tf if hasattr(tf, "sample") else None  # Mann box (oracle/mann_numpy.py); None = uniform inflow
+        # wake-added turbulence (SynchronizedAutoScalingIsotropicMannTurbulence, Wind_Farm_Env.py:618): an object with
+        # a unit-variance isotropic ``field`` (mann_numpy.MannTurbulenceField) advected with the ambient box
+        self.added = getattr(addedTurbulenceModel, "field", None) if self.tf is not None else None
 
     # -- helpers --------------------------------------------------------------------------------
     def slots_by_age(self, t):
@@ -352,6 +366,7 @@ class DWMFlowSimulation:
         # 3. rotor inflow: ambient minus superposed upstream deficits
         du = np.zeros(T)
         dv = np.zeros(T)
+        kmt = np.zeros((T, N_Q))  # sum over wakes of w U0e k_mt at every rotor point (wake-added turbulence)
         for i in range(T):
             n = self.count[i]
             if n < 2:
@@ -380,12 +395,18 @@ class DWMFlowSimulation:
                 U0e, _, cg, sg0 = self.pcon[i, s_].T
                 np.add.at(du, ji, sg_ * wgt * U0e * cg * Dq)
                 np.add.at(dv, ji, sg_ * wgt * U0e * sg0 * Dq)
+                if self.added is not None:
+                    kq = K_M1 * profile_deficit_at(self.prof[i, s_], rq) + K_M2 * profile_gradient_at(self.prof[i, s_], rq)
+                    np.add.at(kmt, ji, (sg_ * wgt * U0e)[:, None] * kq)
         amb = np.zeros((3, T))
         if self.tf is not None:  # rotor-averaged ambient fluctuation at the new time level
             py = self.yr[:, None] + self.qpts[None, :, 0] * R
             pz = self.zh + self.qpts[None, :, 1] * R
             px = np.broadcast_to(self.xr[:, None], py.shape)
             amb = self.tf.sample(px, py, pz, self.time + dt, self.ws).mean(axis=2)
+            if self.added is not None:
+                self.added.offset = self.tf.offset
+                amb = amb + (kmt[None] * self.added.sample(px, py, pz, self.time + dt, self.ws)).mean(axis=2)
         self.rotor_avg_windspeed = np.stack([self.ws + amb[0] - du, amb[1] + dv, amb[2]], axis=1)
         # 4./5. turbine update and particle release
         if self.n_step % self.k_emit == 0:

@@ -212,11 +212,12 @@ class WindFarmEnvOracle:
 
     def __init__(self, turbine, cfg, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.5, turbtype="None",
                  Baseline_comp=False, yaw_init=None, seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True,
-                 eval_mode=False, reset_init=True, noise_seed=0, turb_field=None):
+                 eval_mode=False, reset_init=True, noise_seed=0, turb_field=None, added_field=None):
         if turbtype not in ("None", "MannFixed", "MannGenerate", "MannLoad"):
             raise NotImplementedError("turbtype 'Random' (white-noise field) is not restated")
         self.turbtype = turbtype
         self.turb_field = turb_field      # oracle.mann_numpy.MannTurbulenceField for the Mann site types
+        self.added_field = added_field    # unit-variance isotropic box of the wake-added turbulence (or None)
         self.turb_offset = (0.0, 0.0, 0.0)
         if turbtype != "None" and turb_field is None:
             raise ValueError("a Mann turbtype needs turb_field (the box the device path was given)")
@@ -308,7 +309,10 @@ class WindFarmEnvOracle:
             tf.offset = np.asarray(self.turb_offset, dtype=np.float64)
             tf.scale_TI(TI=self.ti, U=self.ws)
         site = dwm.TurbulenceFieldSite(ws=self.ws, turbulenceField=tf)
-        return dwm.DWMFlowSimulation(site, wts, wind_direction=self.wd, dt=self.dt, d_particle=self.d_particle)
+        import types
+        added = types.SimpleNamespace(field=self.added_field) if self.added_field is not None else None
+        return dwm.DWMFlowSimulation(site, wts, wind_direction=self.wd, dt=self.dt, d_particle=self.d_particle,
+                                     addedTurbulenceModel=added)
 
     def _measure(self):
         uvw = self.fs.windTurbines.rotor_avg_windspeed

@@ -34,11 +34,26 @@ def test_device_generator_matches_oracle(built_lib):
     assert float(big.raw[..., 0].std()) > float(big.raw[..., 1].std()) > float(big.raw[..., 2].std())
 
 
-@pytest.mark.parametrize("reward", ["Power_avg", "Baseline"])
-def test_flow_with_turbulence_box_vs_oracle(built_lib, reward):
+N_ISO = (64, 32, 32)
+
+
+def _iso_boxes():
+    """Unit-variance isotropic box of the wake-added turbulence, oracle (fp64) and device, from the same noise."""
+    from windgym_b200.mann import MannBox
+    noise = mn.box_noise(N_ISO, 23)
+    ref = mn.mann_box(1.0, 10.0, 0.0, N_ISO, (5.0, 5.0, 5.0), noise=noise)
+    ref = ref / ref[0].std()
+    box = MannBox.isotropic_unit(80.0, device="cuda:0", Nxyz=N_ISO, noise=noise)
+    assert abs(float(box.raw[..., 0].double().std(unbiased=False)) - 1.0) < 1e-5
+    return ref, box
+
+
+@pytest.mark.parametrize("reward,added", [("Power_avg", False), ("Baseline", False), ("Power_avg", True), ("Baseline", True)])
+def test_flow_with_turbulence_box_vs_oracle(built_lib, reward, added):
     import torch
     from windgym_b200 import V80, VecWindFarmEnv
     ref_box, box = _boxes()
+    ref_iso, iso = _iso_boxes() if added else (None, False)
     cfg = small_config(2, 2, reward=reward, action="wind")
     B, T, steps = 3, 4, 6
     rng = np.random.default_rng(3)
@@ -46,7 +61,7 @@ def test_flow_with_turbulence_box_vs_oracle(built_lib, reward):
     yaw0 = rng.uniform(-15, 15, (B, T))
     off = rng.uniform(0, 1, (B, 3)) * (np.array(N) * np.array(D3))
     acts = rng.uniform(-1, 1, (steps, B, T)).astype(np.float32)
-    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="MannFixed", turb_box=box)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="MannFixed", turb_box=box, added_turbulence=iso)
     obs0 = env.reset(wind=(ws, ti, wd), yaw0=yaw0, turb_offset=off)[0].cpu().numpy().copy()
     pw, yw, ob, rw, uvw = [], [], [], [], []
     for a in acts:
@@ -60,13 +75,25 @@ def test_flow_with_turbulence_box_vs_oracle(built_lib, reward):
     assert np.abs(uvw[..., 2]).max() > 1e-3 and np.abs(z[z != 0] - 70.0).max() > 0.05   # w' at rotors, wakes meander in z
     for b in range(B):
         field = mn.MannTurbulenceField(ref_box, D3, lowpass_width=160.0)
+        afield = mn.MannTurbulenceField(ref_iso, (5.0, 5.0, 5.0), lowpass_width=5.0) if added else None
         ref = oracle_rollout(cfg, ws[b:b + 1], ti[b:b + 1], wd[b:b + 1], yaw0[b:b + 1], acts[:, b:b + 1],
-                             turbtype="MannFixed", turb_field=field, reset_kw=dict(turb_offset=off[b]))
+                             turbtype="MannFixed", turb_field=field, added_field=afield,
+                             reset_kw=dict(turb_offset=off[b]))
         rel = np.abs(pw[:, b] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
         assert rel.max() < 1e-4, f"env {b}: power rel err {rel.max():.3e}"
         assert np.allclose(obs0[b], ref["obs0"][0], atol=2e-5)
         assert np.allclose(ob[:, b], ref["obs"][0], atol=2e-5)
         assert np.allclose(rw[:, b], ref["reward"][0], rtol=2e-4, atol=2e-5)
+    if added:   # the added turbulence acts inside wakes only: the most upstream rotor is untouched by it
+        env1 = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="MannFixed", turb_box=box,
+                              added_turbulence=False)
+        env1.reset(wind=(ws, ti, wd), yaw0=yaw0, turb_offset=off)
+        for a in acts:
+            env1.step(torch.as_tensor(a))
+        u1 = env1.state["u"][:, 0].cpu().numpy()
+        up_ = env.state["xr"].cpu().numpy().argmin(axis=1)
+        assert np.array_equal(u1[np.arange(B), up_], uvw[-1][np.arange(B), up_, 0])
+        assert np.abs(u1 - uvw[-1][..., 0]).max() > 1e-3
     # turbulence makes the rotor inflow fluctuate: the same farm without a box sees a steady free-stream front row
     env0 = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0")
     env0.reset(wind=(ws, ti, wd), yaw0=yaw0)
@@ -80,6 +107,7 @@ def test_facade_with_mann_box_runs_and_meanders(built_lib):
     _, box = _boxes()
     cfg = small_config(2, 1, reward="Power_avg", action="yaw")
     env = WindFarmEnv(V80(), config=cfg, turbtype="MannGenerate", turb_box=box, seed=2, device="cuda:0")
+    assert env.vec.added_box is not None and env.vec.added_box.Nxyz == (128, 64, 64)   # default addedTurbulenceModel
     obs, info = env.reset(seed=2)
     p = []
     for _ in range(20):

@@ -69,6 +69,8 @@ SYMBOLS = {
     "wg_copy_envs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_set_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_float]),
+    "wg_set_added_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_float]),
     "wg_flow_field": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_float, C.c_void_p, C.c_void_p]),
     "wg_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)]),

@@ -493,7 +493,7 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   if (!h) return fail(WG_ERR_INVALID, "wg_set_turbulence: null argument");
   wg::Dev& d = h->dev;
   if (!raw_uvw0 && !lp_vw) {  // back to uniform inflow
-    d.tb_raw = nullptr; d.tb_lp = nullptr;
+    d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr;
     return WG_OK;
   }
   if (!raw_uvw0 || !lp_vw) return fail(WG_ERR_INVALID, "wg_set_turbulence: both box layouts are required");
@@ -509,6 +509,27 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   d.tb_len_x = (float)((double)nx * (double)dx);
   h->tb_lp_bytes = (size_t)nx * ny * nz * sizeof(float2);
   h->policy_streams.clear();
+  return WG_OK;
+}
+
+int wg_set_added_turbulence(wg_handle* h, const float* iso_uvw0, int32_t nx, int32_t ny, int32_t nz, float dx, float dy,
+                            float dz, float k_m1, float k_m2) {
+  if (!h) return fail(WG_ERR_INVALID, "wg_set_added_turbulence: null argument");
+  wg::Dev& d = h->dev;
+  if (!iso_uvw0) {
+    d.tb2_raw = nullptr;
+    return WG_OK;
+  }
+  if (!d.tb_raw) return fail(WG_ERR_INVALID, "wg_set_added_turbulence: attach the ambient box (wg_set_turbulence) first");
+  if (nx < 2 || ny < 2 || nz < 2 || !(dx > 0.f) || !(dy > 0.f) || !(dz > 0.f))
+    return fail(WG_ERR_INVALID, "wg_set_added_turbulence: box needs >= 2 cells and positive spacing per axis");
+  if ((uintptr_t)iso_uvw0 & 15) return fail(WG_ERR_INVALID, "wg_set_added_turbulence: box must be 16-byte aligned");
+  d.tb2_raw = reinterpret_cast<const float4*>(iso_uvw0);
+  d.tb2_n[0] = nx; d.tb2_n[1] = ny; d.tb2_n[2] = nz;
+  d.tb2_inv_d[0] = 1.f / dx; d.tb2_inv_d[1] = 1.f / dy; d.tb2_inv_d[2] = 1.f / dz;
+  d.tb2_inv_n[0] = 1.f / nx; d.tb2_inv_n[1] = 1.f / ny; d.tb2_inv_n[2] = 1.f / nz;
+  d.tb2_len_x = (float)((double)nx * (double)dx);
+  d.k_m1 = k_m1; d.k_m2 = k_m2;
   return WG_OK;
 }
 

@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(128) wg_flow_field_kernel(const Dev d, int b, 
     }
     float4 amb = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d.tb_raw)
-      amb = sample_raw(d, x, y, z, taylor_shift(d, ws, d.n_step[bf], d.tb_off[b * 3]), d.tb_off[b * 3 + 1],
+      amb = sample_raw(d, x, y, z, taylor_shift(d, ws, d.n_step[bf], d.tb_off[b * 3], d.tb_len_x), d.tb_off[b * 3 + 1],
                        d.tb_off[b * 3 + 2], d.tb_scale[b]);
     out[i] = ws + amb.x - du;
     out[n + i] = amb.y + dv;

@@ -55,13 +55,16 @@ void set_rotor_points(const float* qy, const float* qz) {
 
 // Per-CTA bookkeeping in front of the tile buffers.  TC = turbine capacity of the tables (16 or WG_MAX_T: small
 // farms leave the shared memory to more resident CTAs -- with TC = 16 the CTA needs 37 KB, six fit on an SM).
-template <int TC, bool TURB>
+template <int TC, int TURB>
 struct __align__(16) FlowShared {
   unsigned long long mbar[WG_NWARP];
   float xr[TC], yr[TC], yaw[TC], u[TC], v[TC], w[TC], pw[TC], ct[TC], ind[TC], cg[TC], sg[TC];
   float xs[2 * TC];                         // turbine x sorted ascending, padded with +inf
   float sum_ws[TC], sum_wd[TC], sum_yaw[TC], sum_pw[TC];
   float tu[TURB ? TC : 1], tv[TURB ? TC : 1], tw[TURB ? TC : 1];  // rotor-averaged ambient fluctuation
+  // TURB == 2 (wake-added turbulence): isotropic box sampled at every rotor's quadrature points, per-warp sums
+  float iso[TURB == 2 ? 3 * TC * WG_NQ : 1];
+  float acc_ad[TURB == 2 ? 3 * WG_NWARP * TC : 1];
   float acc_du[WG_NWARP][TC], acc_dv[WG_NWARP][TC];  // per-warp superposed deficit per rotor
   int ord[TC];                              // turbine index of xs[k]
   int head[TC], count[TC], pre[TC + 1], emit_slot[TC];
@@ -72,10 +75,10 @@ struct __align__(16) FlowShared {
   uint32_t hit_b[WG_NWARP][WG_HIT_CAP];     // (shared address of the row ^ (key << 4)) | rotor index j << 20
 };
 
-template <int TC, bool TURB>
+template <int TC, int TURB>
 __host__ __device__ constexpr size_t hdr_bytes() { return (sizeof(FlowShared<TC, TURB>) + 255) / 256 * 256; }
 // six CTAs per SM: 6 x (header + 32 KB of tiles + 1 KB reserved) must fit the 228 KB of the SM
-static_assert(hdr_bytes<16, false>() <= 5120 && hdr_bytes<16, true>() <= 5120, "small-farm header outgrew 5 KB");
+static_assert(hdr_bytes<16, 0>() <= 5120 && hdr_bytes<16, 1>() <= 5120, "small-farm header outgrew 5 KB");
 
 // ---------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -426,7 +429,17 @@ __device__ __forceinline__ Seg segments(const LaneLoc& L, int lane) {
 template <int TC>
 struct RotorAcc {
   float du0, dv0, du1, dv1;
-  __device__ __forceinline__ void clear() { du0 = dv0 = du1 = dv1 = 0.f; }
+  float a0[3], a1[3];  // wake-added turbulence (u, v, w) of rotor l / l + 32 (TURB == 2 only)
+  __device__ __forceinline__ void clear() {
+    du0 = dv0 = du1 = dv1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a0[k] = a1[k] = 0.f;
+  }
+  __device__ __forceinline__ void add_added(int lane, int j, float au, float av, float aw) {
+    if (lane == (j & 31)) {
+      if (TC <= 32 || j < 32) { a0[0] += au; a0[1] += av; a0[2] += aw; } else { a1[0] += au; a1[1] += av; a1[2] += aw; }
+    }
+  }
   __device__ __forceinline__ void add(int lane, int j, float du, float dv) {
     if (TC > 32) {
       if (lane == (j & 31)) {
@@ -440,9 +453,10 @@ struct RotorAcc {
 
 // Evaluate the queued (station row, rotor) hits of one warp: two hits per pass, 16 quadrature points each on
 // 16 lanes, shuffle-reduced to the rotor average.
-template <int TC>
+template <int TC, int TURB>
 __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const uint32_t* __restrict__ hb, int nh,
-                                           RotorAcc<TC>& acc, int lane, float qy, float qz) {
+                                           RotorAcc<TC>& acc, int lane, float qy, float qz, const float* __restrict__ iso,
+                                           float k_m1, float k_m2) {
   const unsigned full = 0xffffffffu;
   const int half = lane >> 4;
   for (int h0 = 0; h0 < nh; h0 += 2) {
@@ -459,7 +473,27 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
     float u1 = lds1(brow ^ ((uint32_t)(j0 + 1) << 2));
     if (j0 == WG_NR - 2) u1 = 1.f;
     float d = fmaf(fr, u0 - u1, 1.f - u0);  // (1-u0)(1-fr) + (1-u1) fr
-    if (s >= (float)(WG_NR - 1) || !ok) d = 0.f;
+    const bool out = s >= (float)(WG_NR - 1) || !ok;
+    if (out) d = 0.f;
+    if (TURB == 2) {
+      // wake-added turbulence: k_mt = k_m1 |1 - U| + k_m2 |dU/dr| at this point, times the station's weight w U0e
+      // (|a.xy| with the sign of a.x: cos g0 > 0) and the isotropic box at (rotor bj, point lane & 15)
+      const float kq = out ? 0.f : fmaf(k_m2, fabsf(u1 - u0) * (1.f / DR), k_m1 * d);
+      const float c = copysignf(sqrtf(fmaf(a.x, a.x, a.y * a.y)), a.x) * kq;
+      const int ip = bj * WG_NQ + (lane & 15);
+      float au = c * iso[ip], av = c * iso[TC * WG_NQ + ip], aw = c * iso[2 * TC * WG_NQ + ip];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        au += __shfl_xor_sync(full, au, o);
+        av += __shfl_xor_sync(full, av, o);
+        aw += __shfl_xor_sync(full, aw, o);
+      }
+      const int jA = __shfl_sync(full, bj, 0), jB = __shfl_sync(full, bj, 16);
+      acc.add_added(lane, jA, __shfl_sync(full, au, 0) * (1.f / WG_NQ), __shfl_sync(full, av, 0) * (1.f / WG_NQ),
+                    __shfl_sync(full, aw, 0) * (1.f / WG_NQ));
+      acc.add_added(lane, jB, __shfl_sync(full, au, 16) * (1.f / WG_NQ), __shfl_sync(full, av, 16) * (1.f / WG_NQ),
+                    __shfl_sync(full, aw, 16) * (1.f / WG_NQ));
+    }
     d += __shfl_xor_sync(full, d, 8);
     d += __shfl_xor_sync(full, d, 4);
     d += __shfl_xor_sync(full, d, 2);
@@ -474,8 +508,9 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
   }
 }
 
-template <int TC, bool TURB>
-__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kernel(const Dev d, const FlowArgs a) {
+template <int TC, int TURB>
+__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) : 4)
+    wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // rows must be 256-byte aligned (XOR addressing)
   typedef FlowShared<TC, TURB> Shared;
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -572,8 +607,17 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
     const float* __restrict__ pm_old = (nstep & 1) ? pmut1 : pmut0;
     float* __restrict__ pm_new = (nstep & 1) ? pmut0 : pmut1;
     // Taylor shift of the turbulence box at the old time level (particle motion) and the new one (rotor inflow)
-    const float xs_t = TURB ? taylor_shift(d, ws, nstep, tb_xo) : 0.f;
-    const float xs_t1 = TURB ? taylor_shift(d, ws, nstep + 1, tb_xo) : 0.f;
+    const float xs_t = TURB ? taylor_shift(d, ws, nstep, tb_xo, d.tb_len_x) : 0.f;
+    const float xs_t1 = TURB ? taylor_shift(d, ws, nstep + 1, tb_xo, d.tb_len_x) : 0.f;
+    if (TURB == 2) {  // the isotropic box at every rotor point, new time level (read by flush_hits after the barrier)
+      const float xs2 = taylor_shift(d, ws, nstep + 1, tb_xo, d.tb2_len_x);
+      for (int idx = tid; idx < T * WG_NQ; idx += blockDim.x) {
+        const int t = idx >> 4;
+        const float4 q = sample_iso(d, sh.xr[t], fmaf(c_qy[idx & 15], R, sh.yr[t]), fmaf(c_qz[idx & 15], R, d.zh), xs2,
+                                    tb_yo, tb_zo);
+        sh.iso[idx] = q.x; sh.iso[TC * WG_NQ + idx] = q.y; sh.iso[2 * TC * WG_NQ + idx] = q.z;
+      }
+    }
 
     if (tid < T) {
       // baseline farm: greedy yaw controller before its flow step (BasicControllers.py:10-73, Wind_Farm_Env.py:949-952)
@@ -738,7 +782,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
             }
             if (split) {
               __syncwarp();
-              flush_hits<TC>(ha, hb, nhA, acc, lane, qy, qz);
+              flush_hits<TC, TURB>(ha, hb, nhA, acc, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
               __syncwarp();
             }
             if (hitB) {
@@ -751,7 +795,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
             }
             const int nh = split ? nhB : nhA + nhB;
             __syncwarp();
-            if (nh > 0) flush_hits<TC>(ha, hb, nh, acc, lane, qy, qz);
+            if (nh > 0) flush_hits<TC, TURB>(ha, hb, nh, acc, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
             __syncwarp();
           }
         }
@@ -767,6 +811,13 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
     if (TC > 32) {
       sh.acc_du[warp][(lane + 32) % TC] = acc.du1;
       sh.acc_dv[warp][(lane + 32) % TC] = acc.dv1;
+    }
+    if (TURB == 2) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (lane < TC) sh.acc_ad[(k * WG_NWARP + warp) * TC + lane] = acc.a0[k];
+        if (TC > 32) sh.acc_ad[(k * WG_NWARP + warp) * TC + (lane + 32) % TC] = acc.a1[k];
+      }
     }
     if (TURB) {  // ambient fluctuation averaged over every rotor's quadrature points at the new time level
       for (int idx = tid; idx < T * WG_NQ; idx += blockDim.x) {  // T*16: half-warps stay whole
@@ -795,7 +846,15 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
       float du = 0.f, dv = 0.f;
 #pragma unroll
       for (int wi = 0; wi < WG_NWARP; ++wi) { du += sh.acc_du[wi][tid]; dv += sh.acc_dv[wi][tid]; }
-      const float u = ws - du + (TURB ? sh.tu[tid] : 0.f), v = dv + (TURB ? sh.tv[tid] : 0.f), w = TURB ? sh.tw[tid] : 0.f;
+      float u = ws - du + (TURB ? sh.tu[tid] : 0.f), v = dv + (TURB ? sh.tv[tid] : 0.f), w = TURB ? sh.tw[tid] : 0.f;
+      if (TURB == 2) {
+#pragma unroll
+        for (int wi = 0; wi < WG_NWARP; ++wi) {
+          u += sh.acc_ad[(0 * WG_NWARP + wi) * TC + tid];
+          v += sh.acc_ad[(1 * WG_NWARP + wi) * TC + tid];
+          w += sh.acc_ad[(2 * WG_NWARP + wi) * TC + tid];
+        }
+      }
       const float yaw = sh.yaw[tid];
       float sg, cg;
       sincosf(yaw * 0.017453292519943295f, &sg, &cg);
@@ -897,7 +956,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? 6 : 4) wg_flow_kerne
   }
 }
 
-template <int TC, bool TURB>
+template <int TC, int TURB>
 static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
   const size_t smem = hdr_bytes<TC, TURB>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES;
   static bool configured = false;
@@ -912,8 +971,9 @@ static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  if (d.tb_raw) return d.T <= 16 ? launch_as<16, true>(d, a, s) : launch_as<WG_MAX_T, true>(d, a, s);
-  return d.T <= 16 ? launch_as<16, false>(d, a, s) : launch_as<WG_MAX_T, false>(d, a, s);
+  if (d.tb_raw && d.tb2_raw) return d.T <= 16 ? launch_as<16, 2>(d, a, s) : launch_as<WG_MAX_T, 2>(d, a, s);
+  if (d.tb_raw) return d.T <= 16 ? launch_as<16, 1>(d, a, s) : launch_as<WG_MAX_T, 1>(d, a, s);
+  return d.T <= 16 ? launch_as<16, 0>(d, a, s) : launch_as<WG_MAX_T, 0>(d, a, s);
 }
 
 }  // namespace wg

@@ -87,6 +87,11 @@ struct Dev {
   float tb_inv_d[3], tb_inv_n[3], tb_len_x;
   float *tb_off;          // [B,3] position of the env inside the box [m]
   float *tb_scale;        // [B]   scale_TI factor
+  // wake-added turbulence: isotropic unit-variance box (u, v, w, 0), advected with the ambient one; null = off
+  const float4* tb2_raw;
+  int tb2_n[3];
+  float tb2_inv_d[3], tb2_inv_n[3], tb2_len_x;
+  float k_m1, k_m2;       // k_mt(r) = k_m1 |1 - U| + k_m2 |dU/dr|
 };
 
 struct FlowArgs {
@@ -126,12 +131,35 @@ __device__ __forceinline__ void wrap_cell(float X, int n, float inv_n, int& i0, 
   i0 = min(max((int)f0, 0), n - 1);  // rounding at the seam can land on -0 / n
   i1 = i0 + 1 == n ? 0 : i0 + 1;
 }
-__device__ __forceinline__ BoxIdx box_index(const Dev& d, float X, float Y, float Z) {
+__device__ __forceinline__ BoxIdx box_index(const int* n, const float* inv_n, float X, float Y, float Z) {
   BoxIdx b;
-  wrap_cell(X, d.tb_n[0], d.tb_inv_n[0], b.i[0], b.i[1], b.fx);
-  wrap_cell(Y, d.tb_n[1], d.tb_inv_n[1], b.j[0], b.j[1], b.fy);
-  wrap_cell(Z, d.tb_n[2], d.tb_inv_n[2], b.k[0], b.k[1], b.fz);
+  wrap_cell(X, n[0], inv_n[0], b.i[0], b.i[1], b.fx);
+  wrap_cell(Y, n[1], inv_n[1], b.j[0], b.j[1], b.fy);
+  wrap_cell(Z, n[2], inv_n[2], b.k[0], b.k[1], b.fz);
   return b;
+}
+__device__ __forceinline__ BoxIdx box_index(const Dev& d, float X, float Y, float Z) {
+  return box_index(d.tb_n, d.tb_inv_n, X, Y, Z);
+}
+// trilinear (u, v, w) of a float4 box at cell coordinates
+__device__ __forceinline__ float4 gather4(const float4* __restrict__ raw, const int* n, const BoxIdx& b) {
+  float u = 0.f, v = 0.f, w = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int bb = 0; bb < 2; ++bb) {
+      const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
+      const float4* rowp = raw + ((size_t)b.i[a] * n[1] + b.j[bb]) * n[2];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const float wt = wxy * (c ? b.fz : 1.f - b.fz);
+        const float4 q = __ldg(rowp + b.k[c]);
+        u = fmaf(wt, q.x, u);
+        v = fmaf(wt, q.y, v);
+        w = fmaf(wt, q.z, w);
+      }
+    }
+  return make_float4(u, v, w, 0.f);
 }
 // low-pass (v, w) at a wake centre; xs = Taylor shift U t - x_off (so that the box x is x - xs)
 __device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
@@ -157,28 +185,19 @@ __device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, floa
 __device__ __forceinline__ float4 sample_raw(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
                                              float scale) {
   const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
-  float u = 0.f, v = 0.f, w = 0.f;
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int bb = 0; bb < 2; ++bb) {
-      const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
-      const float4* rowp = d.tb_raw + ((size_t)b.i[a] * d.tb_n[1] + b.j[bb]) * d.tb_n[2];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const float wt = wxy * (c ? b.fz : 1.f - b.fz);
-        const float4 q = __ldg(rowp + b.k[c]);
-        u = fmaf(wt, q.x, u);
-        v = fmaf(wt, q.y, v);
-        w = fmaf(wt, q.z, w);
-      }
-    }
-  return make_float4(u * scale, v * scale, w * scale, 0.f);
+  const float4 q = gather4(d.tb_raw, d.tb_n, b);
+  return make_float4(q.x * scale, q.y * scale, q.z * scale, 0.f);
+}
+// unit-variance isotropic box of the wake-added turbulence (same offsets, its own periodic length)
+__device__ __forceinline__ float4 sample_iso(const Dev& d, float x, float y, float z, float xs2, float yo, float zo) {
+  const BoxIdx b = box_index(d.tb2_n, d.tb2_inv_n, (x - xs2) * d.tb2_inv_d[0], (y + yo) * d.tb2_inv_d[1],
+                             (z + zo) * d.tb2_inv_d[2]);
+  return gather4(d.tb2_raw, d.tb2_n, b);
 }
 // Taylor shift of the box at flow time t = n dt, reduced modulo the box length in double so that the float
 // coordinate stays small: box x = x - (U t - x_off)
-__device__ __forceinline__ float taylor_shift(const Dev& d, float ws, int n_step, float x_off) {
-  const double s = fmod((double)ws * (double)n_step * (double)d.dt - (double)x_off, (double)d.tb_len_x);
+__device__ __forceinline__ float taylor_shift(const Dev& d, float ws, int n_step, float x_off, float len_x) {
+  const double s = fmod((double)ws * (double)n_step * (double)d.dt - (double)x_off, (double)len_x);
   return (float)s;
 }
 #endif

@@ -263,7 +263,7 @@ class WindFarmEnv(_GymEnv):
     def __init__(self, turbine, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.50, TurbBox="Default", turbtype="None",
                  yaml_path=None, Baseline_comp=False, yaw_init=None, render_mode=None, seed=None, dt_sim=1, dt_env=1,
                  yaw_step=1, fill_window=True, sample_site=None, HTC_path=None, reset_init=True, config=None,
-                 device="cuda:0", turb_box=None):
+                 device="cuda:0", turb_box=None, added_turbulence=None):
         if HTC_path is not None:
             raise NotImplementedError("HAWC2 turbines (HTC_path) are out of scope: external aero-elastic co-simulation")
         if render_mode is not None and render_mode not in self.metadata["render_modes"]:
@@ -274,7 +274,7 @@ class WindFarmEnv(_GymEnv):
                                   Baseline_comp=Baseline_comp, yaw_init=yaw_init, seed=seed, dt_sim=dt_sim,
                                   dt_env=dt_env, yaw_step=yaw_step, fill_window=fill_window, device=device,
                                   multi_agent=self._multi_agent, eval_mode=self._eval_mode, sample_site=sample_site,
-                                  turb_box=turb_box)
+                                  turb_box=turb_box, added_turbulence=added_turbulence)
         self.sample_site = sample_site
         v, ec = self.vec, self.vec.ec
         self.turbine, self.seed = turbine, seed

@@ -129,6 +129,17 @@ class MannBox:
         return cls(uvw, dxyz, lowpass_width=lowpass_width)
 
     @classmethod
+    def isotropic_unit(cls, D, seed=1, device="cuda:0", Nxyz=(128, 64, 64), noise=None):
+        """Box of the wake-added turbulence (``SynchronizedAutoScalingIsotropicMannTurbulence``): isotropic (Gamma = 0),
+        small scales (L = D/8, cells of D/16), normalised to unit standard deviation of u."""
+        box = cls.generate(1.0, D / 8.0, 0.0, Nxyz=Nxyz, dxyz=(D / 16.0,) * 3, seed=seed, device=device, noise=noise,
+                           lowpass_width=D / 16.0)
+        box.raw /= box.std_u
+        box.lp /= box.std_u
+        box.std_u = 1.0
+        return box
+
+    @classmethod
     def from_file(cls, path, device="cuda:0", dxyz=None, lowpass_width=160.0):
         """``MannTurbulenceField.from_netcdf`` (Wind_Farm_Env.py:614-617).  ``.npy`` ([3,Nx,Ny,Nz], needs ``dxyz``),
         ``.npz`` (arrays ``uvw`` and ``dxyz``) or NetCDF-3 through scipy (variables ``uvw`` + coordinate axes)."""

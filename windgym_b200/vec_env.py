@@ -24,7 +24,8 @@ class VecWindFarmEnv:
     def __init__(self, turbine, n_envs, yaml_path=None, config=None, n_passthrough=5, TI_min_mes=0.0,
                  TI_max_mes=0.50, TurbBox="Default", turbtype="None", Baseline_comp=False, yaw_init=None,
                  seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True, device="cuda:0",
-                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None, turb_box=None):
+                 multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None, turb_box=None,
+                 added_turbulence=None):
         cfg = config if config is not None else load_yaml(yaml_path)
         self.ec = ec = EnvConfig(cfg, turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes,
                                  TI_max_mes=TI_max_mes, turbtype=turbtype, Baseline_comp=Baseline_comp,
@@ -50,8 +51,18 @@ class VecWindFarmEnv:
         torch.cuda.set_device(self.device)
         self._create()
         self.turb_box = None
+        self.added_box = None
         if ec.turbtype != "None":
             self._attach_turbulence(turb_box, TurbBox)
+            # addedTurbulenceModel of the Mann site types (Wind_Farm_Env.py:618,:639,:658); a MannBox injects the
+            # isotropic box, False switches the model off
+            if added_turbulence is not False:
+                from .mann import MannBox
+                self.added_box = added_turbulence if isinstance(added_turbulence, MannBox) else \
+                    MannBox.isotropic_unit(ec.D, seed=4321, device=self.device)
+                nx, ny, nz = self.added_box.Nxyz
+                _lib.check(self.lib.wg_set_added_turbulence(self._h, _ptr(self.added_box.raw), nx, ny, nz,
+                                                            *self.added_box.dxyz, 0.6, 0.35))
         self.obs_shape = (self.n_envs, self.n_turb, self.obs_var) if multi_agent else (self.n_envs, self.obs_var)
         self.obs = torch.zeros(self.obs_shape, dtype=torch.float32, device=self.device)
         self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
