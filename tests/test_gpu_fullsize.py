@@ -105,3 +105,39 @@ def test_cfg4_64_turbines_1024_envs_vs_oracle(built_lib):
     rel = np.abs(big["power"][:, 0] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
     assert rel.max() < POWER_RTOL, f"power rel err {rel.max():.3e}"
     assert np.allclose(big["obs"][:, 0], ref["obs"][0], atol=OBS_ATOL)
+
+
+def test_cfg5_multi_agent_2048_envs_rollout_shape_and_oracle(built_lib):
+    """BASELINE.json cfg 5 shape: WindFarmEnvMulti semantics, 4x2 farm (8 agents), 2048 envs, PPO-rollout buffers
+    obs f32[n, 2048, 8, 2] / actions f32[n, 2048, 8, 1]; sampled envs against the oracle's per-agent observations."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    from windgym_b200.vector import collect_rollout
+    nx, ny, T, B, n = 4, 2, 8, 2048, 4
+    cfg = small_config(nx, ny, reward="Power_avg", action="yaw")
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=5)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", multi_agent=True, n_passthrough=20)
+    obs0, _ = env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    assert tuple(obs0.shape) == (B, T, 2)
+    obs0 = obs0.cpu().numpy().copy()
+    gen = torch.Generator(device="cuda:0").manual_seed(3)
+    acts = torch.rand((n, B, T), generator=gen, device="cuda:0") * 2 - 1
+    k = {"i": 0}
+
+    def policy(o):                          # one action per agent from a fixed table (stands in for a shared MLP)
+        a = acts[k["i"]]
+        k["i"] += 1
+        return a
+    ro = collect_rollout(env, policy, n, auto_reset=False)
+    assert tuple(ro["obs"].shape) == (n, B, T, 2) and tuple(ro["actions"].unsqueeze(-1).shape) == (n, B, T, 1)
+    assert tuple(ro["rewards"].shape) == (n, B) and not bool(ro["dones"].any())
+    env.check_flags()
+    sel = [0, 1023, 2047]
+    ref = oracle_rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts.cpu().numpy()[:, sel], multi=True,
+                         n_passthrough=20)
+    got_obs = torch.cat([ro["obs"][1:], ro["last_obs"][None]]).cpu().numpy()      # observation AFTER step i
+    for i, b in enumerate(sel):
+        assert np.allclose(obs0[b], ref["obs0"][i], atol=OBS_ATOL)
+        assert np.allclose(got_obs[:, b], ref["obs"][i], atol=OBS_ATOL)
+        assert np.allclose(ro["rewards"][:, b].cpu().numpy(), ref["reward"][i], rtol=2e-4, atol=2e-5)
+    env.close()

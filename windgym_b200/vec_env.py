@@ -68,6 +68,7 @@ class VecWindFarmEnv:
         self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
         self.truncated = torch.zeros(self.n_envs, dtype=torch.uint8, device=self.device)
         self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=self.device)
+        self._step_ptrs = (_ptr(self._state), _ptr(self.obs), _ptr(self.reward), _ptr(self.truncated))
         # host copies of the per-env wind conditions of the current episode
         self.ws = np.zeros(self.n_envs); self.ti = np.zeros(self.n_envs); self.wd = np.zeros(self.n_envs)
         if reset_init:
@@ -313,12 +314,15 @@ class VecWindFarmEnv:
         """WindFarmEnv.step for every env: actions float32 [B,T] (device) -> obs, reward, terminated, truncated, info."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
-        actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
+            actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         n_act = getattr(self, "n_active", self.n_envs)
         if actions.numel() != n_act * self.n_turb:
             raise ValueError(f"actions must have {n_act}x{self.n_turb} elements")
-        _lib.check(self.lib.wg_step(self._h, _ptr(self._state), _ptr(actions), _ptr(self.obs), _ptr(self.reward),
-                                    _ptr(self.truncated), self._stream()))
+        p = self._step_ptrs  # fixed buffers: the ctypes pointers are built once
+        rc = self.lib.wg_step(self._h, p[0], C.c_void_p(actions.data_ptr()), p[1], p[2], p[3], self._stream())
+        if rc != 0:
+            _lib.check(rc)
         self._last_actions = actions
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
 
@@ -376,7 +380,13 @@ class VecWindFarmEnv:
             raise _lib.WgError("wake particle chain overflow (p_cap too small)")
 
     def _info(self):
-        """Device views with the reference's info keys (Wind_Farm_Env.py:527-555); zero-copy, no sync."""
+        """Device views with the reference's info keys (Wind_Farm_Env.py:527-555); zero-copy, no sync.  The views
+        are live (they always show the current state), so the dict is built once and only the host-side wind
+        conditions are refreshed."""
+        d = getattr(self, "_info_views", None)
+        if d is not None:
+            d["Wind speed Global"], d["Wind direction Global"], d["Turbulence intensity"] = self.ws, self.wd, self.ti
+            return dict(d)
         s = self.state
         d = {
             "yaw angles agent": s["yaw"][:, 0], "Wind speed Global": self.ws, "Wind direction Global": self.wd,
@@ -388,7 +398,8 @@ class VecWindFarmEnv:
             d["yaw angles base"] = s["yaw"][:, 1]
             d["Power pr turbine baseline"] = s["power"][:, 1]
             d["Wind speed at turbines baseline"] = s["u"][:, 1]
-        return d
+        self._info_views = d
+        return dict(d)
 
     # helpers for tests / inspection ------------------------------------------------------------------------
     def profiles_by_age(self, b, f, t):

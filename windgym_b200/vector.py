@@ -213,3 +213,29 @@ class RecordEpisodeVals:
             self.episode_powers[idx] = 0.0
             self.episode_start_times[idx] = now
         return obs, rewards, terminations, truncations, infos
+
+
+def collect_rollout(venv, policy, n_steps, auto_reset=True):
+    """PPO-style rollout buffer on the device: ``policy(obs) -> actions`` is called on the env's own tensors, nothing
+    leaves the GPU.  Returns ``obs [n, B, ...]``, ``actions [n, B, T]``, ``rewards [n, B]``, ``dones [n, B]`` and the
+    observation after the last step.  Works for the single-agent layout (obs [B, obs_var]) and the multi-agent one
+    (``multi_agent=True``: obs [B, T, obs_var], one action per agent -- BASELINE.json cfg 5: obs f32[128, 2048, 8, 2],
+    actions f32[128, 2048, 8, 1] after ``unsqueeze(-1)``)."""
+    B, T, dev = venv.n_envs, venv.n_turb, venv.device
+    obs = venv.obs
+    buf_obs = torch.empty((n_steps,) + tuple(obs.shape), dtype=torch.float32, device=dev)
+    buf_act = torch.empty((n_steps, B, T), dtype=torch.float32, device=dev)
+    buf_rew = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
+    buf_done = torch.empty((n_steps, B), dtype=torch.bool, device=dev)
+    for i in range(n_steps):
+        buf_obs[i] = obs
+        act = policy(obs).reshape(B, T).to(torch.float32)
+        buf_act[i] = act
+        obs, rew, term, trunc, _ = venv.step(act)
+        buf_rew[i], buf_done[i] = rew, trunc.bool()
+        if auto_reset:
+            done = trunc.cpu().numpy().astype(bool)
+            if done.any():
+                venv.reset(mask=done)
+                obs = venv.obs
+    return {"obs": buf_obs, "actions": buf_act, "rewards": buf_rew, "dones": buf_done, "last_obs": obs.clone()}
