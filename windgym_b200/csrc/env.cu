@@ -79,7 +79,7 @@ __device__ float calc_ti(Get get, int L) {
 // read instead of dependent global loads inside the serial window sums); pushes go to both copies.
 #define WG_FIN_WARPS 4
 template <bool STAGE>
-__global__ void __launch_bounds__(WG_FIN_WARPS * 32) wg_finish_kernel(const Dev d, const FinishArgs a) {
+__global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const Dev d, const FinishArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
   const int b = blockIdx.x * WG_FIN_WARPS + warp;
   if (b >= d.Bg) return;
