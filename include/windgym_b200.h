@@ -77,6 +77,12 @@ typedef struct {
   int32_t action_penalty_type; /* 0 "Change", 1 "Total" (:804-820)           */
   int32_t steps_on_reset; /* (:229-240)                                      */
   wg_mes_config mes;
+  /* Extension (no reference counterpart: act_var = 1 there, TODO at Wind_Farm_Env.py:43,:97-99; BASELINE.json cfg 4
+   * "yaw + induction actions"): act_var = 2 appends one derating action per turbine, actions [B, 2T] =
+   * [yaw actions | induction actions]; u in [-1, 1] sets the induction scale delta = derate_min + (u+1)/2 (1 - derate_min):
+   * a = delta a_tab, CT = 4a(1-a) cos^2(yaw), P = P_tab a(1-a)^2 / (a_tab (1-a_tab)^2).  act_var = 0 means 1. */
+  int32_t act_var;
+  float derate_min;
 } wg_config;
 
 /* Per-env inputs of WindFarmEnv.reset (Wind_Farm_Env.py:680-802).  All device pointers.  The integer fields are

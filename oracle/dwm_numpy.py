@@ -245,13 +245,37 @@ class PyWakeWindTurbines:
     def rotor_avg_windspeed(self):
         return self._fs.rotor_avg_windspeed
 
+    # Extension (no reference counterpart; BASELINE.json cfg 4 "yaw + induction actions"): ``derate`` scales every
+    # rotor's axial induction, a = delta a_tab: CT = 4a(1-a) cos^2(yaw), P = P_tab a(1-a)^2 / (a_tab (1-a_tab)^2).
+    # delta = 1 is the reference's turbine (and takes the reference's code path, bit for bit).
+    def _derated(self):
+        u = self._fs.rotor_avg_windspeed[:, 0]
+        co = np.cos(np.deg2rad(self._yaw))
+        p_tab = self.windTurbine.power(u * co, yaw=0.0)
+        ct_tab = np.clip(self.windTurbine.ct(u * co, yaw=0.0), 0.0, CT_MAX)
+        a0 = 0.5 * (1.0 - np.sqrt(1.0 - ct_tab))
+        a1 = self.derate * a0
+        with np.errstate(divide="ignore", invalid="ignore"):
+            scale = np.where(a0 > 0, (a1 * (1 - a1) ** 2) / (a0 * (1 - a0) ** 2), 1.0)
+        return p_tab * scale, 4.0 * a1 * (1.0 - a1) * co**2
+
     def power(self):
+        der = getattr(self, "derate", None)
+        if der is not None and np.any(der != 1.0):
+            p, _ = self._derated()
+            full = self.windTurbine.power(self._fs.rotor_avg_windspeed[:, 0], yaw=self._yaw)
+            return np.where(der != 1.0, p, full)
         u = self._fs.rotor_avg_windspeed[:, 0]
         return self.windTurbine.power(u, yaw=self._yaw)
 
     def ct(self):
         u = self._fs.rotor_avg_windspeed[:, 0]
-        return np.minimum(self.windTurbine.ct(u, yaw=self._yaw), CT_MAX)
+        full = np.minimum(self.windTurbine.ct(u, yaw=self._yaw), CT_MAX)
+        der = getattr(self, "derate", None)
+        if der is not None and np.any(der != 1.0):
+            _, c = self._derated()
+            return np.where(der != 1.0, np.minimum(c, CT_MAX), full)
+        return full
 
 
 def rotate_layout(x, y, wd):

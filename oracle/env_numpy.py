@@ -212,10 +212,13 @@ class WindFarmEnvOracle:
 
     def __init__(self, turbine, cfg, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.5, turbtype="None",
                  Baseline_comp=False, yaw_init=None, seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True,
-                 eval_mode=False, reset_init=True, noise_seed=0, turb_field=None, added_field=None):
+                 eval_mode=False, reset_init=True, noise_seed=0, turb_field=None, added_field=None,
+                 induction_control=False, derate_min=0.5):
         if turbtype not in ("None", "MannFixed", "MannGenerate", "MannLoad"):
             raise NotImplementedError("turbtype 'Random' (white-noise field) is not restated")
         self.turbtype = turbtype
+        self.act_var = 2 if induction_control else 1   # extension: [yaw actions | induction actions]
+        self.derate_min = derate_min
         self.turb_field = turb_field      # oracle.mann_numpy.MannTurbulenceField for the Mann site types
         self.added_field = added_field    # unit-variance isotropic box of the wake-added turbulence (or None)
         self.turb_offset = (0.0, 0.0, 0.0)
@@ -401,6 +404,10 @@ class WindFarmEnvOracle:
 
     def _adjust_yaws(self, action):
         wt = self.fs.windTurbines
+        if self.act_var == 2:  # extension: the second half of the action vector sets the induction scale
+            ua = np.asarray(action[self.n_turb:], dtype=np.float64)
+            wt.derate = np.clip(self.derate_min + 0.5 * (ua + 1.0) * (1.0 - self.derate_min), self.derate_min, 1.0)
+            action = action[:self.n_turb]
         if self.ActionMethod == "yaw":
             wt.yaw = np.clip(wt.yaw + action * self.yaw_step, self.yaw_min, self.yaw_max)
         elif self.ActionMethod == "wind":

@@ -93,15 +93,16 @@ def test_cfg4_64_turbines_1024_envs_vs_oracle(built_lib):
     ws, ti, wd, yaw0 = _conditions(B, T, seed=64)
     ws = np.clip(ws, 11, 15)
     ws[1], ti[1], wd[1], yaw0[1] = ws[0], ti[0], wd[0], yaw0[0]
-    acts = np.random.default_rng(8).uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    # cfg 4 is "yaw + induction actions": [yaw | induction] per env (act_var = 2 extension)
+    acts = np.random.default_rng(8).uniform(-1, 1, (steps, B, 2 * T)).astype(np.float32)
     acts[:, 1] = acts[:, 0]
-    big, live, xr = _rollout(cfg, ws, ti, wd, yaw0, acts, fill_window=2)
+    big, live, xr = _rollout(cfg, ws, ti, wd, yaw0, acts, fill_window=2, induction_control=True)
     assert np.array_equal(big["power"][:, 1], big["power"][:, 0])
     assert np.isfinite(big["power"]).all() and big["power"].min() >= 0.0 and big["power"].max() <= 2.0e6 + 1.0
     up = xr.argmin(axis=1)
-    assert np.allclose(big["u"][-1][np.arange(B), up], ws, rtol=1e-6)
+    assert np.allclose(big["u"][-1][np.arange(B), up], ws, rtol=1e-6)   # derating changes P and CT, not the inflow
     sel = [0]
-    ref = oracle_rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts[:, sel], fill_window=2)
+    ref = oracle_rollout(cfg, ws[sel], ti[sel], wd[sel], yaw0[sel], acts[:, sel], fill_window=2, induction_control=True)
     rel = np.abs(big["power"][:, 0] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
     assert rel.max() < POWER_RTOL, f"power rel err {rel.max():.3e}"
     assert np.allclose(big["obs"][:, 0], ref["obs"][0], atol=OBS_ATOL)

@@ -93,6 +93,34 @@ def test_step_parity_substeps_and_penalty(built_lib):
     _compare(gpu, ref, B)
 
 
+def test_induction_action_extension_parity(built_lib):
+    """act_var = 2 (extension; BASELINE.json cfg 4 'yaw + induction actions'): [yaw | induction] actions, derated
+    rotors a = delta a_tab -- against the oracle's turbine model; delta = 1 reproduces the yaw-only run exactly."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    cfg = small_config(2, 2, reward="Baseline", action="wind")
+    B, T, steps = 3, 4, 8
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=31)
+    rng = np.random.default_rng(6)
+    acts = rng.uniform(-1, 1, (steps, B, 2 * T)).astype(np.float32)
+    env, gpu = _run_gpu(cfg, ws, ti, wd, yaw0, acts, induction_control=True, derate_min=0.4)
+    assert env.ec.act_var == 2
+    der = env.state["derate"][:, 0].cpu().numpy()
+    assert np.allclose(der, 0.4 + 0.5 * (acts[-1][:, T:] + 1.0) * 0.6, atol=1e-6) and (env.state["derate"][:, 1] == 1).all()
+    ref = oracle_rollout(cfg, ws, ti, wd, yaw0, acts, induction_control=True, derate_min=0.4)
+    _compare(gpu, ref, B, baseline=True)
+    # derating costs power at the derated rotor: compare with the same yaw actions and delta = 1
+    full = acts.copy()
+    full[:, :, T:] = 1.0
+    _, gpu1 = _run_gpu(cfg, ws, ti, wd, yaw0, full, induction_control=True, derate_min=0.4)
+    _, gpu0 = _run_gpu(cfg, ws, ti, wd, yaw0, acts[:, :, :T])
+    assert np.array_equal(gpu1["power"], gpu0["power"]) and np.array_equal(gpu1["obs"], gpu0["obs"])
+    up = env.state["xr"].cpu().numpy().argmin(axis=1)
+    assert (gpu["power"][-1][np.arange(B), up] <= gpu0["power"][-1][np.arange(B), up] + 1e-3).all()
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((B, T)))
+
+
 def test_rich_observation_parity(built_lib):
     """All measurement channels, current + several windows, TI, farm level (MesClass.py:328-351, :679-703)."""
     cfg = rich_config(2, 2, reward="Power_avg")

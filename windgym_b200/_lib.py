@@ -39,7 +39,7 @@ class Config(C.Structure):
                 ("action_method", C.c_int32), ("yaw_min", C.c_float), ("yaw_max", C.c_float), ("yaw_step", C.c_float),
                 ("base_controller", C.c_int32), ("power_reward", C.c_int32), ("power_avg", C.c_int32),
                 ("power_scaling", C.c_float), ("action_penalty", C.c_float), ("action_penalty_type", C.c_int32),
-                ("steps_on_reset", C.c_int32), ("mes", MesConfig)]
+                ("steps_on_reset", C.c_int32), ("mes", MesConfig), ("act_var", C.c_int32), ("derate_min", C.c_float)]
 
 
 class ResetArgs(C.Structure):

@@ -57,6 +57,8 @@ class EnvConfig:
     eval_mode: bool = False
     multi_agent: bool = False
     noise_seed: int = 0
+    induction_control: bool = False   # extension: one derating action per turbine after the yaw actions
+    derate_min: float = 0.5
     derived: dict = field(default_factory=dict)
 
     def __post_init__(self):
@@ -64,6 +66,9 @@ class EnvConfig:
         if self.dt_env % self.dt_sim != 0:
             raise ValueError("dt_env must be a multiple of dt_sim")
         self.S = int(self.dt_env / self.dt_sim)
+        self.act_var = 2 if self.induction_control else 1
+        if not (0.0 < self.derate_min <= 1.0):
+            raise ValueError("derate_min must be in (0, 1]")
         if self.turbtype == "Random":
             raise NotImplementedError("turbtype='Random' (white-noise RandomTurbulence field) is not built; use a Mann "
                                       "box type or 'None'")

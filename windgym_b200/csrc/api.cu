@@ -116,6 +116,7 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.w = at<float>(state, h, "w");
   d.power = at<float>(state, h, "power");
   d.ct = at<float>(state, h, "ct");
+  d.derate = at<float>(state, h, "derate");
   d.ws = at<float>(state, h, "ws");
   d.ti = at<float>(state, h, "ti");
   d.wd = at<float>(state, h, "wd");
@@ -241,6 +242,9 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   if (cfg->n_farms == 2 && (cfg->base_controller < 0 || cfg->base_controller > 1))
     return fail(WG_ERR_INVALID, "The BaseController must be either Local or Global... For now");
   if (cfg->power_avg < 1) return fail(WG_ERR_INVALID, "Power_avg must be >= 1");
+  if (cfg->act_var < 0 || cfg->act_var > 2) return fail(WG_ERR_INVALID, "act_var must be 1 (yaw) or 2 (yaw + induction)");
+  if (cfg->act_var == 2 && !(cfg->derate_min > 0.f && cfg->derate_min <= 1.f))
+    return fail(WG_ERR_INVALID, "derate_min must be in (0, 1]");
   const wg_mes_channel* ch[4] = {&cfg->mes.ws, &cfg->mes.wd, &cfg->mes.yaw, &cfg->mes.power};
   for (int c = 0; c < 4; ++c)
     if (ch[c]->history_length < 1 || ch[c]->window_length < 1 || ch[c]->history_N < 1)
@@ -305,6 +309,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   d.dt = cfg->dt; d.D = cfg->diameter; d.R = 0.5f * cfg->diameter; d.zh = cfg->hub_height; d.d_particle = cfg->d_particle;
   d.yaw_min = cfg->yaw_min; d.yaw_max = cfg->yaw_max; d.yaw_step = cfg->yaw_step;
   d.action_method = cfg->action_method; d.base_controller = cfg->base_controller;
+  d.act_var = cfg->act_var == 2 ? 2 : 1; d.derate_min = cfg->derate_min;
   d.power_reward = cfg->power_reward; d.power_avg = cfg->power_avg; d.pen_type = cfg->action_penalty_type;
   d.power_scaling = cfg->power_scaling; d.action_penalty = cfg->action_penalty;
   d.n_rings = (int)ring_off.size(); d.ring_floats = off; d.obs_dim = obs_dim; d.obs_rows = obs_rows;
@@ -325,7 +330,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "head", 1, {B, F, T});
   add_field(h, "count", 1, {B, F, T});
   add_field(h, "n_step", 1, {B, F});
-  for (const char* n : {"yaw", "u", "v", "w", "power", "ct"}) add_field(h, n, 0, {B, F, T});
+  for (const char* n : {"yaw", "u", "v", "w", "power", "ct", "derate"}) add_field(h, n, 0, {B, F, T});
   for (const char* n : {"ws", "ti", "wd", "rated_power", "xmax", "base_pow_mean"}) add_field(h, n, 0, {B});
   for (const char* n : {"k_emit", "time_max", "timestep", "flags", "n_push", "n_fp", "n_bp", "spin"})
     add_field(h, n, 1, {B});

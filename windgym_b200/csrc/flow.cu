@@ -540,15 +540,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   void* bar = &sh.mbar[warp];
   const bool tab_sh = d.n_tab <= WG_TAB_CAP;
 
+  float der_r = 1.f;  // induction scale of turbine tid (act_var = 2 extension); lives in its thread
   if (tid < T) {
     sh.xr[tid] = d.xr[b * T + tid];
     sh.yr[tid] = d.yr[b * T + tid];
     sh.xs[tid] = d.xs_sorted[b * T + tid];
     sh.ord[tid] = d.ord_sorted[b * T + tid];
     float yaw = d.yaw[bf * T + tid];
+    der_r = d.derate[bf * T + tid];
     if (a.mode == FLOW_STEP && f == 0 && a.actions) {  // _adjust_yaws, Wind_Farm_Env.py:822-864
       d.old_yaw[b * T + tid] = yaw;
-      float act = a.actions[b * T + tid];
+      float act = a.actions[b * T * d.act_var + tid];
+      if (d.act_var == 2) {  // extension: induction (derating) action, applied as set point
+        const float ua = a.actions[b * T * 2 + T + tid];
+        der_r = fminf(fmaxf(d.derate_min + 0.5f * (ua + 1.f) * (1.f - d.derate_min), d.derate_min), 1.f);
+      }
       if (d.action_method == 0) {
         yaw = fminf(fmaxf(yaw + act * d.yaw_step, d.yaw_min), d.yaw_max);
       } else {
@@ -861,6 +867,13 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       const float wse = u * cg;
       float pw, ct;
       tab_interp2(tws, tpw, tct, d.n_tab, wse, pw, ct);
+      const float der = der_r;
+      if (der != 1.f) {  // derated rotor: a = delta a_tab (actuator disc), see include/windgym_b200.h
+        const float ctt = fminf(fmaxf(ct, 0.f), CT_MAX);
+        const float a0 = 0.5f * (1.f - sqrtf(1.f - ctt)), a1 = der * a0;
+        ct = 4.f * a1 * (1.f - a1);
+        if (a0 > 0.f) pw *= (a1 * (1.f - a1) * (1.f - a1)) / (a0 * (1.f - a0) * (1.f - a0));
+      }
       ct *= cg * cg;
       ct = fminf(fmaxf(ct, 0.f), CT_MAX);
       sh.u[tid] = u; sh.v[tid] = v; sh.w[tid] = w; sh.pw[tid] = pw; sh.ct[tid] = ct;
@@ -931,6 +944,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 
   if (tid < T) {
     d.yaw[bf * T + tid] = sh.yaw[tid];
+    d.derate[bf * T + tid] = der_r;
     d.u[bf * T + tid] = sh.u[tid];
     d.v[bf * T + tid] = sh.v[tid];
     d.w[bf * T + tid] = sh.w[tid];

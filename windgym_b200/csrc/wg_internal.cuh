@@ -47,6 +47,8 @@ struct Dev {
   float dt, D, R, zh, d_particle;
   float yaw_min, yaw_max, yaw_step;
   int action_method, base_controller;
+  int act_var;            // 1: yaw actions; 2: + one induction (derating) action per turbine (extension)
+  float derate_min;
   int power_reward, power_avg, pen_type;
   float power_scaling, action_penalty;
   // mes
@@ -69,6 +71,7 @@ struct Dev {
   int* head; int* count;  // [B,F,T]
   int* n_step;            // [B,F]
   float *yaw, *u, *v, *w, *power, *ct;  // [B,F,T]
+  float *derate;          // [B,F,T] induction scale delta in [derate_min, 1] (1 = the reference's turbine)
   // env state
   float *ws, *ti, *wd, *rated, *xmax;   // [B]
   int *k_emit, *time_max, *timestep, *flags, *n_push, *n_fp, *n_bp, *spin;  // [B]

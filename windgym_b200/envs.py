@@ -263,7 +263,7 @@ class WindFarmEnv(_GymEnv):
     def __init__(self, turbine, n_passthrough=5, TI_min_mes=0.0, TI_max_mes=0.50, TurbBox="Default", turbtype="None",
                  yaml_path=None, Baseline_comp=False, yaw_init=None, render_mode=None, seed=None, dt_sim=1, dt_env=1,
                  yaw_step=1, fill_window=True, sample_site=None, HTC_path=None, reset_init=True, config=None,
-                 device="cuda:0", turb_box=None, added_turbulence=None):
+                 device="cuda:0", turb_box=None, added_turbulence=None, induction_control=False, derate_min=0.5):
         if HTC_path is not None:
             raise NotImplementedError("HAWC2 turbines (HTC_path) are out of scope: external aero-elastic co-simulation")
         if render_mode is not None and render_mode not in self.metadata["render_modes"]:
@@ -274,7 +274,8 @@ class WindFarmEnv(_GymEnv):
                                   Baseline_comp=Baseline_comp, yaw_init=yaw_init, seed=seed, dt_sim=dt_sim,
                                   dt_env=dt_env, yaw_step=yaw_step, fill_window=fill_window, device=device,
                                   multi_agent=self._multi_agent, eval_mode=self._eval_mode, sample_site=sample_site,
-                                  turb_box=turb_box, added_turbulence=added_turbulence)
+                                  turb_box=turb_box, added_turbulence=added_turbulence,
+                                  induction_control=induction_control, derate_min=derate_min)
         self.sample_site = sample_site
         v, ec = self.vec, self.vec.ec
         self.turbine, self.seed = turbine, seed
@@ -284,7 +285,7 @@ class WindFarmEnv(_GymEnv):
         self.TI_min, self.TI_max = ec.TI_min, ec.TI_max
         self.Baseline_comp, self.ActionMethod, self.BaseController = ec.Baseline_comp, ec.ActionMethod, ec.BaseController
         self.dt_sim, self.dt_env, self.sim_steps_per_env_step = dt_sim, dt_env, ec.S
-        self.act_var = 1
+        self.act_var = ec.act_var   # 1 in the reference (Wind_Farm_Env.py:97-99); 2 with induction_control
         self.obs_var = v.obs_var
         self.hist_max, self.steps_on_reset = ec.hist_max, ec.steps_on_reset
         self.maxturbpower = ec.maxturbpower
@@ -363,8 +364,8 @@ class WindFarmEnv(_GymEnv):
     def step(self, action):
         """Wind_Farm_Env.py:920-1034.  Returns (obs, reward, terminated=False, truncated, info)."""
         a = np.asarray(action, dtype=np.float32).reshape(1, -1)
-        if a.shape[1] != self.n_turb:
-            raise ValueError(f"action must have {self.n_turb} entries")
+        if a.shape[1] != self.n_turb * self.act_var:
+            raise ValueError(f"action must have {self.n_turb * self.act_var} entries")
         obs, rew, _, trunc, _ = self.vec.step(torch.as_tensor(a))
         fl = int(self.vec.state["flags"][0])
         if fl & 1:

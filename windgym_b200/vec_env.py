@@ -25,13 +25,13 @@ class VecWindFarmEnv:
                  TI_max_mes=0.50, TurbBox="Default", turbtype="None", Baseline_comp=False, yaw_init=None,
                  seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True, device="cuda:0",
                  multi_agent=False, eval_mode=False, noise_seed=0, reset_init=False, sample_site=None, turb_box=None,
-                 added_turbulence=None):
+                 added_turbulence=None, induction_control=False, derate_min=0.5):
         cfg = config if config is not None else load_yaml(yaml_path)
         self.ec = ec = EnvConfig(cfg, turbine, n_passthrough=n_passthrough, TI_min_mes=TI_min_mes,
                                  TI_max_mes=TI_max_mes, turbtype=turbtype, Baseline_comp=Baseline_comp,
                                  yaw_init=yaw_init, dt_sim=dt_sim, dt_env=dt_env, yaw_step=yaw_step,
                                  fill_window=fill_window, eval_mode=eval_mode, multi_agent=multi_agent,
-                                 noise_seed=noise_seed)
+                                 noise_seed=noise_seed, induction_control=induction_control, derate_min=derate_min)
         self.turbine = turbine
         self.n_envs, self.n_turb = int(n_envs), ec.n_turb
         self.device = torch.device(device)
@@ -110,7 +110,7 @@ class VecWindFarmEnv:
             yaw_step=float(ec.yaw_step), base_controller=codes["controller"], power_reward=codes["reward"],
             power_avg=int(ec.power_avg), power_scaling=float(ec.Power_scaling),
             action_penalty=float(ec.action_penalty), action_penalty_type=codes["penalty"],
-            steps_on_reset=int(ec.steps_on_reset), mes=mes)
+            steps_on_reset=int(ec.steps_on_reset), mes=mes, act_var=int(ec.act_var), derate_min=float(ec.derate_min))
         h = C.c_void_p()
         _lib.check(self.lib.wg_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -317,8 +317,8 @@ class VecWindFarmEnv:
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
         n_act = getattr(self, "n_active", self.n_envs)
-        if actions.numel() != n_act * self.n_turb:
-            raise ValueError(f"actions must have {n_act}x{self.n_turb} elements")
+        if actions.numel() != n_act * self.n_turb * self.ec.act_var:
+            raise ValueError(f"actions must have {n_act}x{self.n_turb * self.ec.act_var} elements")
         p = self._step_ptrs  # fixed buffers: the ctypes pointers are built once
         rc = self.lib.wg_step(self._h, p[0], C.c_void_p(actions.data_ptr()), p[1], p[2], p[3], self._stream())
         if rc != 0:
@@ -394,6 +394,8 @@ class VecWindFarmEnv:
             "Wind speed at turbines": s["meas"][:, 0], "Wind direction at turbines": s["meas"][:, 1],
             "Turbine x positions": s["xr"], "Turbine y positions": s["yr"],
         }
+        if self.ec.act_var == 2:
+            d["derating agent"] = s["derate"][:, 0]
         if self.Baseline_comp:
             d["yaw angles base"] = s["yaw"][:, 1]
             d["Power pr turbine baseline"] = s["power"][:, 1]
