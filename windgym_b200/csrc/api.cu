@@ -2,6 +2,7 @@
 // Host-side only; the kernels live in flow.cu and env.cu.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -48,6 +49,11 @@ struct wg_handle {
   wg::CopyField* d_copy = nullptr;
   int n_copy = 0;
   int n_active = 0;  // envs stepped by wg_step (prefix of the allocation; the rest is the spare pool)
+  // longest-first launch order of wg_step (state field "order"): rebuilt when stale
+  const void* order_state = nullptr;  // state tensor the current order was built for (null: rebuild)
+  int order_n = 0;                    // ... and its active count
+  int order_age = 0;                  // wg_step calls since the last rebuild
+  bool use_order = true;              // WG_NO_ORDER=1 in the environment: plain index order (A/B measurements)
   // L2 residency of the turbulence box: streams that already carry the access-policy window
   std::vector<cudaStream_t> policy_streams;
   size_t tb_lp_bytes = 0;
@@ -110,6 +116,8 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.head = at<int>(state, h, "head");
   d.count = at<int>(state, h, "count");
   d.n_step = at<int>(state, h, "n_step");
+  d.load = at<int>(state, h, "load");
+  d.order = at<int>(state, h, "order");
   d.yaw = at<float>(state, h, "yaw");
   d.u = at<float>(state, h, "u");
   d.v = at<float>(state, h, "v");
@@ -306,6 +314,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   memset(&d, 0, sizeof(d));
   d.B = B; d.Bg = B; d.T = T; d.F = F; d.P = P; d.S = cfg->substeps; d.n_tab = cfg->n_tab;
   h->n_active = B;
+  const char* no_order = getenv("WG_NO_ORDER");
+  h->use_order = !(no_order && no_order[0] == '1');
   d.dt = cfg->dt; d.D = cfg->diameter; d.R = 0.5f * cfg->diameter; d.zh = cfg->hub_height; d.d_particle = cfg->d_particle;
   d.yaw_min = cfg->yaw_min; d.yaw_max = cfg->yaw_max; d.yaw_step = cfg->yaw_step;
   d.action_method = cfg->action_method; d.base_controller = cfg->base_controller;
@@ -330,6 +340,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "head", 1, {B, F, T});
   add_field(h, "count", 1, {B, F, T});
   add_field(h, "n_step", 1, {B, F});
+  add_field(h, "load", 1, {B, F});
   for (const char* n : {"yaw", "u", "v", "w", "power", "ct", "derate"}) add_field(h, n, 0, {B, F, T});
   for (const char* n : {"ws", "ti", "wd", "rated_power", "xmax", "base_pow_mean"}) add_field(h, n, 0, {B});
   for (const char* n : {"k_emit", "time_max", "timestep", "flags", "n_push", "n_fp", "n_bp", "spin"})
@@ -345,7 +356,6 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "rings", 0, {B, off});
   add_field(h, "farm_pow_ring", 0, {B, cfg->power_avg});
   add_field(h, "base_pow_ring", 0, {B, cfg->power_avg});
-  h->state_bytes = (h->state_bytes + 255) / 256 * 256;
   // field table of the env-copy kernel: leading dimension B, or [2, B, ...] for the ping-pong buffer
   std::vector<wg::CopyField> cf;
   for (auto& f : h->fields) {
@@ -358,6 +368,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
     cf.push_back(c);
   }
   h->n_copy = (int)cf.size();
+  add_field(h, "order", 1, {B});  // a permutation of the active envs, not per-env state: outside the copy table
+  h->state_bytes = (h->state_bytes + 255) / 256 * 256;
   if ((e = upload(&h->d_copy, cf.data(), cf.size())) != cudaSuccess) {
     wg_destroy(h);
     return cuda_fail(e, "wg_create upload");
@@ -413,6 +425,8 @@ int wg_launch_count(const wg_handle* h, uint64_t* out) {
     if (e_ != cudaSuccess) return cuda_fail(e_, what);          \
   } while (0)
 
+#define WG_ORDER_PERIOD 64
+
 int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream) {
   if (!h || !state) return fail(WG_ERR_INVALID, "wg_flow_steps: null argument");
   if (n_steps < 0) return fail(WG_ERR_INVALID, "n_steps must be >= 0");
@@ -431,6 +445,7 @@ int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, v
     return fail(WG_ERR_INVALID, "wg_reset: every per-env input array is required");
   cudaStream_t s = (cudaStream_t)cuda_stream;
   pin_turbulence_in_l2(h, s);
+  h->order_state = nullptr;
   wg::Dev d = bind(h, state);
   if (h->dev.tb_raw && (!args->tb_offset || !args->tb_scale))
     return fail(WG_ERR_INVALID, "wg_reset: a handle with a turbulence box needs tb_offset and tb_scale");
@@ -467,6 +482,12 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   pin_turbulence_in_l2(h, s);
   wg::Dev d = bind(h, state);
   d.Bg = h->n_active;
+  // launch order: rebuilt after a reset / env copy / change of the active set, and every WG_ORDER_PERIOD steps (the
+  // live-station counts drift slowly); more CTAs than resident slots is the only case where the order matters
+  if (h->use_order && (h->order_state != state || h->order_n != d.Bg || ++h->order_age >= WG_ORDER_PERIOD)) {
+    WG_LAUNCH(wg::launch_order(d, s), "wg_order_kernel");
+    h->order_state = state; h->order_n = d.Bg; h->order_age = 0;
+  }
   cudaEvent_t* ev = nullptr;
   if (h->profiling) {
     if (h->prof_used + 3 > h->prof_events.size()) {
@@ -483,6 +504,7 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   }
   wg::FlowArgs fa{};
   fa.mode = wg::FLOW_STEP; fa.actions = actions; fa.farm_mask = (1 << d.F) - 1; fa.controller_on = 1;
+  fa.order = h->use_order ? d.order : nullptr;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
   if (ev) cudaEventRecord(ev[1], s);
   wg::FinishArgs fin{};
@@ -549,6 +571,7 @@ int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* d
   if (!h || !state || !src || !dst) return fail(WG_ERR_INVALID, "wg_copy_envs: null argument");
   if (n < 0) return fail(WG_ERR_INVALID, "n must be >= 0");
   if (n == 0) return WG_OK;
+  h->order_state = nullptr;
   WG_LAUNCH(wg::launch_copy_envs(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, src, dst, n,
                                  (cudaStream_t)cuda_stream),
             "wg_copy_envs_kernel");

@@ -326,6 +326,61 @@ __global__ void __launch_bounds__(256) wg_copy_envs_kernel(unsigned char* __rest
   }
 }
 
+// Launch order of wg_step: the active envs sorted by descending work (live stations over the env's farms), so that
+// the CTAs left over when the grid drains are the short ones (4096 CTAs on 888 resident slots: a greedy
+// longest-first schedule ends within half a short CTA of the ideal, a random one within a long CTA).
+// One CTA, counting sort over WG_ORDER_BINS load classes; the order inside a class is arbitrary (envs are
+// independent: the launch order never changes a result).
+#define WG_ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) wg_order_kernel(const int* __restrict__ load, int F, int Bg, int quantum,
+                                                        int* __restrict__ order) {
+  __shared__ int hist[WG_ORDER_BINS];
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  hist[tid] = 0;
+  __syncthreads();
+  for (int b = tid; b < Bg; b += blockDim.x) {
+    int n = 0;
+    for (int f = 0; f < F; ++f) n += max(load[b * F + f], 0);
+    atomicAdd(&hist[WG_ORDER_BINS - 1 - min(n / quantum, WG_ORDER_BINS - 1)], 1);  // bin 0 = heaviest class
+  }
+  __syncthreads();
+  // exclusive scan of the 1024 bins: warp scan, then the 32 warp totals
+  const int v = hist[tid];
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = wsum[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  hist[tid] = wsum[warp] + inc - v;
+  __syncthreads();
+  for (int b = tid; b < Bg; b += blockDim.x) {
+    int n = 0;
+    for (int f = 0; f < F; ++f) n += max(load[b * F + f], 0);
+    order[atomicAdd(&hist[WG_ORDER_BINS - 1 - min(n / quantum, WG_ORDER_BINS - 1)], 1)] = b;
+  }
+}
+
+cudaError_t launch_order(const Dev& d, cudaStream_t s) {
+  const int most = d.F * d.T * d.P;  // stations an env can hold
+  wg_order_kernel<<<1, 1024, 0, s>>>(d.load, d.F, d.Bg, (most + WG_ORDER_BINS - 1) / WG_ORDER_BINS, d.order);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_copy_envs(unsigned char* state, const CopyField* fields, int n_fields, const int* src, const int* dst,
                              int n, cudaStream_t s) {
   for (int k0 = 0; k0 < n; k0 += 65535) {

@@ -517,7 +517,9 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const int T = d.T, P = d.P, F = d.F;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x / F, f = blockIdx.x % F;
+  // wg_step launches the envs longest first (a.order): the CTAs that drain the grid are then the short ones
+  const int bi = blockIdx.x / F, f = blockIdx.x % F;
+  const int b = a.order ? a.order[bi] : bi;
   const int bf = b * F + f;
   if (a.mask && !a.mask[b]) return;
   if (!((a.farm_mask >> f) & 1)) return;
@@ -962,6 +964,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   }
   if (tid == 0) {
     d.n_step[bf] = nstep;
+    d.load[bf] = sh.pre[T];
     if (a.mode == FLOW_STEP && f == 1) d.base_pow_mean[b] = sh.base_sum / (float)nsteps;
   }
   if (warp == 0) {  // every warp's last TMEM access precedes the substep loop's closing barrier

@@ -70,6 +70,8 @@ struct Dev {
   float* pcon;   // [B,F,T,P,4]    U0e, knu1, cos g0, sin g0
   int* head; int* count;  // [B,F,T]
   int* n_step;            // [B,F]
+  int* load;              // [B,F] live stations of the farm after its last flow step (work estimate of its CTA)
+  int* order;             // [B]   launch order of wg_step: envs [0, Bg) sorted by descending load (see wg_order_kernel)
   float *yaw, *u, *v, *w, *power, *ct;  // [B,F,T]
   float *derate;          // [B,F,T] induction scale delta in [derate_min, 1] (1 = the reference's turbine)
   // env state
@@ -104,6 +106,7 @@ struct FlowArgs {
   const float* actions; // FLOW_STEP: [B,T] or null (reset fill)
   int farm_mask;        // bit f set: farm f advances
   int controller_on;    // baseline farm applies its greedy controller each substep
+  const int* order;     // optional permutation of [0, Bg): CTA group i works on env order[i] (longest first)
 };
 
 struct FinishArgs {
@@ -208,6 +211,7 @@ __device__ __forceinline__ float taylor_shift(const Dev& d, float ws, int n_step
 void set_rotor_points(const float* qy, const float* qz);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
+cudaError_t launch_order(const Dev& d, cudaStream_t s);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
 // one state field as the env-copy kernel sees it: n_rep blocks of B envs, per_env bytes each
 struct CopyField {
