@@ -314,7 +314,8 @@ def run_gpu(a):
         env.step(acts_p[i])
     flow_ms, fin_ms, n_prof = env.profile_read()
     env.profile_enable(False)
-    live = int(env.state["count"].sum().item())          # live wake stations of this rank (all envs, farms, chains)
+    # live wake stations of this rank (all envs, farms, chains): the ring counts minus the stations the next step drops
+    live = int(env.state["count"].sum().item()) - int(env.state["retire"].sum().item())
     F, S = env.n_farms, env.ec.S
     # with a turbulence box every station also gathers 8 corners x 8 B of the low-pass box (not counted as
     # algorithmic state traffic: the box is shared and L2-resident at this size)

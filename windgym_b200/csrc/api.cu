@@ -115,6 +115,7 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.pcon = at<float>(state, h, "pcon");
   d.head = at<int>(state, h, "head");
   d.count = at<int>(state, h, "count");
+  d.retire = at<int>(state, h, "retire");
   d.n_step = at<int>(state, h, "n_step");
   d.load = at<int>(state, h, "load");
   d.order = at<int>(state, h, "order");
@@ -339,6 +340,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "pcon", 0, {B, F, T, P, 4});
   add_field(h, "head", 1, {B, F, T});
   add_field(h, "count", 1, {B, F, T});
+  add_field(h, "retire", 1, {B, F, T});
   add_field(h, "n_step", 1, {B, F});
   add_field(h, "load", 1, {B, F});
   for (const char* n : {"yaw", "u", "v", "w", "power", "ct", "derate"}) add_field(h, n, 0, {B, F, T});

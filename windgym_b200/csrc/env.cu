@@ -252,7 +252,7 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
     const float yaw0 = a.yaw0[b * T + tid];
     for (int f = 0; f < d.F; ++f) {
       const int i = (b * d.F + f) * T + tid;
-      d.head[i] = 0; d.count[i] = 0;
+      d.head[i] = 0; d.count[i] = 0; d.retire[i] = 0;
       d.yaw[i] = yaw0; d.u[i] = ws; d.v[i] = 0.f; d.w[i] = 0.f; d.power[i] = 0.f; d.ct[i] = 0.f; d.derate[i] = 1.f;
     }
     d.old_yaw[b * T + tid] = yaw0;

@@ -38,6 +38,9 @@ namespace wg {
 #define WG_HIT_CAP 32     // per-warp hit list entries (one detection pass of one interval kind adds at most 32)
 #define WG_TAB_CAP 32     // P/CT table knots staged in shared memory (longer tables are read from global)
 #define WG_TMEM_COLS 64
+// squared centre distance (rotor radii) beyond which a wake profile cannot reach any rotor quadrature point
+#define R_CULL2 (((WG_NR - 1) * DR + 1.01f) * ((WG_NR - 1) * DR + 1.01f))
+#define WG_RETIRE_CAP 8   // stations per chain and step that can retire (physically one, two when the wake compresses)
 
 __constant__ float c_qy[WG_NQ];
 __constant__ float c_qz[WG_NQ];
@@ -67,7 +70,10 @@ struct __align__(16) FlowShared {
   float acc_ad[TURB == 2 ? 3 * WG_NWARP * TC : 1];
   float acc_du[WG_NWARP][TC], acc_dv[WG_NWARP][TC];  // per-warp superposed deficit per rotor
   int ord[TC];                              // turbine index of xs[k]
-  int head[TC], count[TC], pre[TC + 1], emit_slot[TC];
+  int head[TC], count[TC], pre[TC + 1];
+  // tile loop: index (from the oldest) of the chain's first station that stays in the farm after the NEXT step's
+  // move (atomicMin by the lanes that march them) -> the stations to retire next step; release: slot of the new particle
+  int keep_emit[TC];
   float base_sum;
   uint32_t tmem_base;                       // TMEM allocation of the CTA
   float tab_ws[WG_TAB_CAP], tab_p[WG_TAB_CAP], tab_ct[WG_TAB_CAP];
@@ -508,6 +514,16 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
   }
 }
 
+#ifdef WG_TRACE
+// diagnostic build (scripts/gpu_trace.sh): per-CTA start / end time and SM of the last FLOW_STEP launch
+__device__ unsigned long long g_trace[8 * 65536];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <int TC, int TURB>
 __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) : 4)
     wg_flow_kernel(const Dev d, const FlowArgs a) {
@@ -521,6 +537,13 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const int bi = blockIdx.x / F, f = blockIdx.x % F;
   const int b = a.order ? a.order[bi] : bi;
   const int bf = b * F + f;
+#ifdef WG_TRACE
+  const unsigned long long t_start = gtimer();
+  unsigned long long t_p1 = 0, t_p2 = 0, t_p3 = 0, t_p4 = 0;
+#define WG_STAMP(v) v = gtimer()
+#else
+#define WG_STAMP(v)
+#endif
   if (a.mask && !a.mask[b]) return;
   if (!((a.farm_mask >> f) & 1)) return;
   int nsteps = (a.mode == FLOW_FIXED) ? a.n_fixed : (a.mode == FLOW_SPIN ? d.spin[b] : d.S);
@@ -543,6 +566,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const bool tab_sh = d.n_tab <= WG_TAB_CAP;
 
   float der_r = 1.f;  // induction scale of turbine tid (act_var = 2 extension); lives in its thread
+  int retire_r = 0;   // oldest stations of chain tid to drop at the head of the next flow step (found in this one)
   if (tid < T) {
     sh.xr[tid] = d.xr[b * T + tid];
     sh.yr[tid] = d.yr[b * T + tid];
@@ -573,6 +597,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     sh.ct[tid] = d.ct[bf * T + tid];
     sh.head[tid] = d.head[bf * T + tid];
     sh.count[tid] = d.count[bf * T + tid];
+    retire_r = d.retire[bf * T + tid];
     sh.sum_ws[tid] = sh.sum_wd[tid] = sh.sum_yaw[tid] = sh.sum_pw[tid] = 0.f;
   }
   if (tab_sh)
@@ -593,6 +618,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  WG_STAMP(t_p1);
   const uint32_t taddr = sh.tmem_base + ((uint32_t)(warp * 32) << 16);
   const float* tws = tab_sh ? sh.tab_ws : d.tab_ws;
   const float* tpw = tab_sh ? sh.tab_p : d.tab_p;
@@ -641,29 +667,33 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         }
         sh.yaw[tid] = yaw;
       }
-      // retire stations that will be past the farm (+margin) after this step's move
-      int cnt = sh.count[tid];
-      const int hd = sh.head[tid];
-      while (cnt > 0) {
-        int s = hd - cnt;
-        if (s < 0) s += P;
-        float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + ((size_t)tid * P + s) * 4));
-        float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + ((size_t)tid * P + s) * 4));
-        float xn, yn, zn, dx;
-        moved(pm, pc, ws, dt, tv0, xn, yn, zn, dx);  // only x matters here: the ambient (v', w') does not move it
-        if (xn > x_retire) --cnt; else break;
-      }
-      sh.count[tid] = cnt;
+      // Retire the stations that are past the farm (+margin) after this step's move.  The oracle tests the moved
+      // position of the oldest stations at the head of the step (oracle/dwm_numpy.py:step, retire loop); the same
+      // test was evaluated by the lanes that marched those stations in the previous step (keep_emit below), so the
+      // head of the step needs no dependent loads.
+      const int c = sh.count[tid] - min(retire_r, sh.count[tid]);
+      sh.count[tid] = c;
+      sh.keep_emit[tid] = min(c, WG_RETIRE_CAP);
     }
-    __syncthreads();
-    if (tid == 0) {
-      int s = 0;
-      for (int t = 0; t < T; ++t) { sh.pre[t] = s; s += sh.count[t]; }
-      sh.pre[T] = s;
+    if (TC > 32) __syncthreads(); else __syncwarp();
+    if (warp == 0) {  // chain offsets in the flat station list: warp scan of the counts
+      const int c0 = lane < T ? sh.count[lane] : 0;
+      const int c1 = (TC > 32 && lane + 32 < T) ? sh.count[lane + 32] : 0;
+      int i0 = c0, i1 = c1;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t0 = __shfl_up_sync(full, i0, o), t1 = __shfl_up_sync(full, i1, o);
+        if (lane >= o) { i0 += t0; i1 += t1; }
+      }
+      const int tot0 = __shfl_sync(full, i0, 31);
+      if (lane == 0) sh.pre[0] = 0;
+      if (lane < T) sh.pre[lane + 1] = i0;
+      if (TC > 32 && lane + 32 < T) sh.pre[lane + 33] = tot0 + i1;
     }
     __syncthreads();
     const int ntot = sh.pre[T];
     const int ntiles = (ntot + WG_TILE - 1) / WG_TILE;
+    WG_STAMP(t_p2);
 
     // ------------------------------------------------------------------ warp-private tile pipeline
     RotorAcc<TC> acc;
@@ -721,8 +751,19 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
+#ifdef WG_EXP_NOMARCH  // timing experiment only: rows pass through unchanged
+        const float ucn = pmc.w + 0.f * (xt_mid + (float)rowk + (float)taddr);
+#else
         const float ucn = march_row_tmem(rowk, taddr, dx * rR, xt_mid, pcc.y);
-        if (Lc.valid) *reinterpret_cast<float4*>(pm_new + st_c * 4u) = make_float4(xn, yn, zn, ucn);
+#endif
+        if (Lc.valid) {
+          *reinterpret_cast<float4*>(pm_new + st_c * 4u) = make_float4(xn, yn, zn, ucn);
+          if (Lc.q < WG_RETIRE_CAP) {  // does this station leave the farm with the next step's move?
+            float x2, y2, z2, dx2;
+            moved(make_float4(xn, yn, zn, ucn), pcc, ws, dt, tv0, x2, y2, z2, dx2);
+            if (!(x2 > x_retire)) atomicMin(&sh.keep_emit[Lc.chain], Lc.q);
+          }
+        }
       }
       fence_async_smem();
       __syncwarp();
@@ -770,22 +811,41 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         if (!has_o) co = cn;
         if (!has_y) cy = cn;
         const int a_lo = min(cn, co), nA = abs(cn - co), b_lo = min(cn, cy), nB = abs(cn - cy);
+#ifdef WG_EXP_NOSUPER  // timing experiment only: no rotor-plane hits
+        const int nmax = 0;
+#else
         const int nmax = __reduce_max_sync(full, max(nA, nB));
+#endif
         if (nmax > 0) {
           const float rdA = rcp_fast(xo - xn), rdB = rcp_fast(xn - xy);
           for (int it = 0; it < nmax; ++it) {
             const int kA = a_lo + it, kB = b_lo + it;
             const int jA = it < nA ? sh.ord[kA] : Lc.chain, jB = it < nB ? sh.ord[kB] : Lc.chain;
-            const bool hitA = jA != Lc.chain, hitB = jB != Lc.chain;
-            const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
-            const int nhA = __popc(mA), nhB = __popc(mB);
-            const bool split = nhA + nhB > WG_HIT_CAP;  // rare: evaluate the two interval kinds one after the other
+            // A wake whose centre passes the rotor centre at >= (WG_NR - 1) dr + 1 rotor radii puts every quadrature
+            // point (|q| < 1) outside its profile: such a hit adds exactly zero and is dropped here.
+            bool hitA = jA != Lc.chain, hitB = jB != Lc.chain;
+            float4 recA, recB;
             if (hitA) {
               const float w = (sh.xs[kA] - xn) * rdA;
               const float wg = kA >= cn ? 1.f - w : w - 1.f;
               const float yc = fmaf(w, yo - yn, yn), zc = fmaf(w, zo - zn, zn);
+              recA = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
+              hitA = fmaf(recA.z, recA.z, recA.w * recA.w) < R_CULL2;
+            }
+            if (hitB) {
+              const float w = (sh.xs[kB] - xy) * rdB;
+              const float wg = kB >= cy ? w : -w;
+              const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
+              recB = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
+              hitB = fmaf(recB.z, recB.z, recB.w * recB.w) < R_CULL2;
+            }
+            const unsigned mA = __ballot_sync(full, hitA), mB = __ballot_sync(full, hitB);
+            const int nhA = __popc(mA), nhB = __popc(mB);
+            if (nhA + nhB == 0) continue;
+            const bool split = nhA + nhB > WG_HIT_CAP;  // rare: evaluate the two interval kinds one after the other
+            if (hitA) {
               const int p = __popc(mA & lt);
-              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jA] - yc) * rR, (d.zh - zc) * rR);
+              ha[p] = recA;
               hb[p] = rowk | ((uint32_t)jA << 20);
             }
             if (split) {
@@ -794,11 +854,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
               __syncwarp();
             }
             if (hitB) {
-              const float w = (sh.xs[kB] - xy) * rdB;
-              const float wg = kB >= cy ? w : -w;
-              const float yc = fmaf(w, yn - yy, yy), zc = fmaf(w, zn - zy, zy);
               const int p = (split ? 0 : nhA) + __popc(mB & lt);
-              ha[p] = make_float4(wg * u0cg, wg * u0sg, (sh.yr[jB] - yc) * rR, (d.zh - zc) * rR);
+              ha[p] = recB;
               hb[p] = rowk | ((uint32_t)jB << 20);
             }
             const int nh = split ? nhB : nhA + nhB;
@@ -812,6 +869,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
       __syncwarp();
     }
+    WG_STAMP(t_p3);
     if (lane < TC) {
       sh.acc_du[warp][lane] = acc.du0;
       sh.acc_dv[warp][lane] = acc.dv0;
@@ -848,6 +906,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     fence_async_all();
     __syncthreads();
 
+    WG_STAMP(t_p4);
     // ------------------------------------------------------------------ turbine epilogue
     const bool emit = (nstep % k_emit) == 0;
     if (tid < T) {
@@ -880,6 +939,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       ct = fminf(fmaxf(ct, 0.f), CT_MAX);
       sh.u[tid] = u; sh.v[tid] = v; sh.w[tid] = w; sh.pw[tid] = pw; sh.ct[tid] = ct;
       sh.cg[tid] = cg; sh.sg[tid] = sg;
+      retire_r = sh.keep_emit[tid];  // length of the chain's prefix (oldest first) that retires next step
       int slot = -1;
       if (emit) {
         sh.ind[tid] = 0.5f * (1.f - sqrtf(1.f - ct));
@@ -887,7 +947,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         if (sh.count[tid] == P) atomicOr(&d.flags[b], 2); else sh.count[tid] += 1;
         sh.head[tid] = (slot + 1 == P) ? 0 : slot + 1;
       }
-      sh.emit_slot[tid] = slot;
+      sh.keep_emit[tid] = slot;
       if (a.mode == FLOW_STEP) {
         if (f == 0) {  // _take_measurements, Wind_Farm_Env.py:480-495
           sh.sum_ws[tid] += sqrtf(u * u + v * v + w * w);
@@ -908,7 +968,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       // turbine write one 16-byte chunk each and shuffle-reduce the row's shear integral into slot 63.
       for (int idx = tid; idx < T * (WG_NR / 4); idx += blockDim.x) {  // T*16 is a multiple of 16: half-warps stay whole
         const int t = idx >> 4, c = idx & 15;
-        const int slot = sh.emit_slot[t];
+        const int slot = sh.keep_emit[t];
         const float ind = sh.ind[t];
         const float fw = 1.f - 0.45f * ind * ind;
         const float rw2 = fw * fw * (1.f - ind) / (1.f - 2.f * ind);
@@ -947,6 +1007,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   if (tid < T) {
     d.yaw[bf * T + tid] = sh.yaw[tid];
     d.derate[bf * T + tid] = der_r;
+    d.retire[bf * T + tid] = retire_r;
     d.u[bf * T + tid] = sh.u[tid];
     d.v[bf * T + tid] = sh.v[tid];
     d.w[bf * T + tid] = sh.w[tid];
@@ -963,6 +1024,16 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     }
   }
   if (tid == 0) {
+#ifdef WG_TRACE
+    if (a.mode == FLOW_STEP && blockIdx.x < 65536) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      unsigned long long* tr = g_trace + 8 * blockIdx.x;
+      tr[0] = t_start; tr[1] = gtimer(); tr[2] = smid;
+      tr[3] = ((unsigned long long)b << 32) | (unsigned)sh.pre[T];
+      tr[4] = t_p1; tr[5] = t_p2; tr[6] = t_p3; tr[7] = t_p4;
+    }
+#endif
     d.n_step[bf] = nstep;
     d.load[bf] = sh.pre[T];
     if (a.mode == FLOW_STEP && f == 1) d.base_pow_mean[b] = sh.base_sum / (float)nsteps;
@@ -986,6 +1057,12 @@ static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
   wg_flow_kernel<TC, TURB><<<d.Bg * d.F, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }
+
+#ifdef WG_TRACE
+extern "C" int wg_debug_trace_read(unsigned long long* out, int n_cta) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 8 * n_cta);
+}
+#endif
 
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s) {
   if (d.tb_raw && d.tb2_raw) return d.T <= 16 ? launch_as<16, 2>(d, a, s) : launch_as<WG_MAX_T, 2>(d, a, s);

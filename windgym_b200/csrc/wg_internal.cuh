@@ -68,7 +68,8 @@ struct Dev {
   float* prof;   // [B,F,T,P,64]   16-byte chunks XOR-swizzled with (slot & 7)
   float* pmut;   // [2,B,F,T,P,4]  x, y, z, uc ; ping-pong on the farm's step parity
   float* pcon;   // [B,F,T,P,4]    U0e, knu1, cos g0, sin g0
-  int* head; int* count;  // [B,F,T]
+  int* head; int* count;  // [B,F,T]  ring buffer per chain; count includes the stations about to retire:
+  int* retire;            // [B,F,T]  oldest stations of the chain that the next flow step drops before it moves
   int* n_step;            // [B,F]
   int* load;              // [B,F] live stations of the farm after its last flow step (work estimate of its CTA)
   int* order;             // [B]   launch order of wg_step: envs [0, Bg) sorted by descending load (see wg_order_kernel)
