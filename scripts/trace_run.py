@@ -25,10 +25,20 @@ def main():
     env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", n_passthrough=bench.n_passthrough_for(200, cfg), seed=0)
     env.reset(wind=(ws, ti, wd), yaw0=yaw0)
     acts = (torch.rand((40, B, T), generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
+    lib = _lib.load()
+    phb = np.zeros(8, dtype=np.uint64)
     for i in range(40):
+        if i == 39:
+            torch.cuda.synchronize()
+            lib.wg_debug_phase_read(phb.ctypes.data_as(C.c_void_p), C.c_int(1))
         env.step(acts[i])
     torch.cuda.synchronize()
-    lib = _lib.load()
+    lib.wg_debug_phase_read(phb.ctypes.data_as(C.c_void_p), C.c_int(0))
+    tot = float(phb.sum())
+    for name, v in zip(("outside the tile loop", "tile set-up (segments, load issue, scalars, prefetch)", "wait for the tile",
+                        "move + march", "store issue + superposition", "wait for the store to release the buffer",
+                        "after the tile loop (barrier, epilogue, release, write-back)"), phb):
+        print(f"  warp time: {name:55s} {float(v) / tot * 100:5.1f} %")
     n = B * env.n_farms
     buf = np.zeros((n, 8), dtype=np.uint64)
     rc = lib.wg_debug_trace_read(buf.ctypes.data_as(C.c_void_p), C.c_int(n))

@@ -517,6 +517,7 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
 #ifdef WG_TRACE
 // diagnostic build (scripts/gpu_trace.sh): per-CTA start / end time and SM of the last FLOW_STEP launch
 __device__ unsigned long long g_trace[8 * 65536];
+__device__ unsigned long long g_phase[8 * 4 * 16384];  // SM cycles per (CTA, warp, phase): see WG_PHASE call sites
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -541,19 +542,52 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const unsigned long long t_start = gtimer();
   unsigned long long t_p1 = 0, t_p2 = 0, t_p3 = 0, t_p4 = 0;
 #define WG_STAMP(v) v = gtimer()
+  long long ph_last = clock64();
+#define WG_PHASE(k)                                                         \
+  if (lane == 0) {                                                          \
+    const long long now_ = clock64();                                       \
+    atomicAdd(&g_phase[((blockIdx.x & 16383) * 4 + warp) * 8 + k], (unsigned long long)(now_ - ph_last));           \
+    ph_last = now_;                                                         \
+  }
 #else
 #define WG_STAMP(v)
+#define WG_PHASE(k)
 #endif
-  if (a.mask && !a.mask[b]) return;
   if (!((a.farm_mask >> f) & 1)) return;
-  int nsteps = (a.mode == FLOW_FIXED) ? a.n_fixed : (a.mode == FLOW_SPIN ? d.spin[b] : d.S);
+  // ---- prologue: every global load of the CTA is issued before the first use of any of them (one round trip to
+  // L2 / HBM instead of a chain of them: each dependent group costs 0.6 - 0.8 us while the CTA holds its slot)
+  const bool is_t = tid < T;
+  const int it = bf * T + (is_t ? tid : 0), jt = b * T + (is_t ? tid : 0);
+  const bool take_action = a.mode == FLOW_STEP && f == 0 && a.actions != nullptr;
+  const bool tab_sh = d.n_tab <= WG_TAB_CAP;
+  const bool tab_mine = tab_sh && tid < d.n_tab;  // tables of up to 32 knots: one knot per thread
+  const uint8_t g_mask = a.mask ? a.mask[b] : (uint8_t)1;
+  const int g_spin = a.mode == FLOW_SPIN ? d.spin[b] : 0;
+  const float ws = d.ws[b], wd = d.wd[b], xmax = d.xmax[b], ti = d.ti[b];
+  const int g_kemit = d.k_emit[b];
+  int nstep = d.n_step[bf];
+  float g_xr = 0.f, g_yr = 0.f, g_xs = 0.f, g_yaw = 0.f, g_der = 1.f, g_u = 0.f, g_v = 0.f, g_w = 0.f, g_pw = 0.f, g_ct = 0.f;
+  float g_act = 0.f, g_act2 = 0.f, g_tws = 0.f, g_tp = 0.f, g_tct = 0.f;
+  int g_ord = 0, g_head = 0, g_count = 0, g_retire = 0;
+  if (is_t) {
+    g_xr = d.xr[jt]; g_yr = d.yr[jt]; g_xs = d.xs_sorted[jt]; g_ord = d.ord_sorted[jt];
+    g_yaw = d.yaw[it]; g_der = d.derate[it];
+    g_u = d.u[it]; g_v = d.v[it]; g_w = d.w[it]; g_pw = d.power[it]; g_ct = d.ct[it];
+    g_head = d.head[it]; g_count = d.count[it]; g_retire = d.retire[it];
+    if (take_action) {
+      g_act = a.actions[b * T * d.act_var + tid];
+      if (d.act_var == 2) g_act2 = a.actions[b * T * 2 + T + tid];
+    }
+  }
+  if (tab_mine) { g_tws = d.tab_ws[tid]; g_tp = d.tab_p[tid]; g_tct = d.tab_ct[tid]; }
+  if (!g_mask) return;
+  const int nsteps = (a.mode == FLOW_FIXED) ? a.n_fixed : (a.mode == FLOW_SPIN ? g_spin : d.S);
   if (nsteps <= 0) return;
 
-  const float ws = d.ws[b], wd = d.wd[b], dt = d.dt, R = d.R, xmax = d.xmax[b];
+  const float dt = d.dt, R = d.R;
   const float rR = 1.f / R;
-  const float ti = d.ti[b];
   const float knu1_env = ti > 0.f ? K1 * powf(ti, 0.3f) : 0.f;
-  const int k_emit = max(d.k_emit[b], 1);
+  const int k_emit = max(g_kemit, 1);
   float* __restrict__ prof = d.prof + (size_t)bf * T * P * WG_NR;
   float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;
   float* pmut0 = d.pmut + (size_t)bf * T * P * 4;
@@ -563,23 +597,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const uint32_t row_a = tile_a + (uint32_t)lane * WG_ROW_BYTES;
   const float qy = c_qy[lane & 15], qz = c_qz[lane & 15];
   void* bar = &sh.mbar[warp];
-  const bool tab_sh = d.n_tab <= WG_TAB_CAP;
 
   float der_r = 1.f;  // induction scale of turbine tid (act_var = 2 extension); lives in its thread
   int retire_r = 0;   // oldest stations of chain tid to drop at the head of the next flow step (found in this one)
-  if (tid < T) {
-    sh.xr[tid] = d.xr[b * T + tid];
-    sh.yr[tid] = d.yr[b * T + tid];
-    sh.xs[tid] = d.xs_sorted[b * T + tid];
-    sh.ord[tid] = d.ord_sorted[b * T + tid];
-    float yaw = d.yaw[bf * T + tid];
-    der_r = d.derate[bf * T + tid];
-    if (a.mode == FLOW_STEP && f == 0 && a.actions) {  // _adjust_yaws, Wind_Farm_Env.py:822-864
+  if (is_t) {
+    sh.xr[tid] = g_xr;
+    sh.yr[tid] = g_yr;
+    sh.xs[tid] = g_xs;
+    sh.ord[tid] = g_ord;
+    float yaw = g_yaw;
+    der_r = g_der;
+    if (take_action) {  // _adjust_yaws, Wind_Farm_Env.py:822-864
       d.old_yaw[b * T + tid] = yaw;
-      float act = a.actions[b * T * d.act_var + tid];
+      const float act = g_act;
       if (d.act_var == 2) {  // extension: induction (derating) action, applied as set point
-        const float ua = a.actions[b * T * 2 + T + tid];
-        der_r = fminf(fmaxf(d.derate_min + 0.5f * (ua + 1.f) * (1.f - d.derate_min), d.derate_min), 1.f);
+        der_r = fminf(fmaxf(d.derate_min + 0.5f * (g_act2 + 1.f) * (1.f - d.derate_min), d.derate_min), 1.f);
       }
       if (d.action_method == 0) {
         yaw = fminf(fmaxf(yaw + act * d.yaw_step, d.yaw_min), d.yaw_max);
@@ -590,22 +622,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       }
     }
     sh.yaw[tid] = yaw;
-    sh.u[tid] = d.u[bf * T + tid];
-    sh.v[tid] = d.v[bf * T + tid];
-    sh.w[tid] = d.w[bf * T + tid];
-    sh.pw[tid] = d.power[bf * T + tid];
-    sh.ct[tid] = d.ct[bf * T + tid];
-    sh.head[tid] = d.head[bf * T + tid];
-    sh.count[tid] = d.count[bf * T + tid];
-    retire_r = d.retire[bf * T + tid];
+    sh.u[tid] = g_u;
+    sh.v[tid] = g_v;
+    sh.w[tid] = g_w;
+    sh.pw[tid] = g_pw;
+    sh.ct[tid] = g_ct;
+    sh.head[tid] = g_head;
+    sh.count[tid] = g_count;
+    retire_r = g_retire;
     sh.sum_ws[tid] = sh.sum_wd[tid] = sh.sum_yaw[tid] = sh.sum_pw[tid] = 0.f;
   }
-  if (tab_sh)
-    for (int i = tid; i < d.n_tab; i += blockDim.x) {
-      sh.tab_ws[i] = d.tab_ws[i];
-      sh.tab_p[i] = d.tab_p[i];
-      sh.tab_ct[i] = d.tab_ct[i];
-    }
+  if (tab_mine) {
+    sh.tab_ws[tid] = g_tws;
+    sh.tab_p[tid] = g_tp;
+    sh.tab_ct[tid] = g_tct;
+  }
   if (tid == 0) sh.base_sum = 0.f;
   if (warp == 0) tmem_alloc(&sh.tmem_base);
   for (int i = T + tid; i < 2 * TC; i += blockDim.x) sh.xs[i] = CUDART_INF_F;
@@ -613,7 +644,6 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  int nstep = d.n_step[bf];
   uint32_t phase = 0;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -701,6 +731,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     LaneLoc Ln;
     Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
     if (warp < ntiles) Ln = locate(sh, warp, lane, T, P, ntot);
+    WG_PHASE(0)  // outside the tile loop (prologue, step head, barriers, epilogue)
     for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
       const LaneLoc Lc = Ln;
       const Seg sg = segments(Lc, lane);
@@ -741,8 +772,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         }
       }
       const uint32_t rowk = row_a ^ ((uint32_t)(Lc.slot & 7) << 4);
+      WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches
       mbar_wait(bar, phase);
       phase ^= 1u;
+      WG_PHASE(2)  // waiting for the tile
       float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
       if (Lc.valid) {
         const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
@@ -765,6 +798,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
           }
         }
       }
+      WG_PHASE(3)  // move + march
       fence_async_smem();
       __syncwarp();
       if (sg.start) {  // write the marched rows back (same segments as the load)
@@ -866,8 +900,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         }
       }
       __syncwarp();
+      WG_PHASE(4)  // store issue + superposition
       bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
       __syncwarp();
+      WG_PHASE(5)  // waiting for the store to release the buffer
     }
     WG_STAMP(t_p3);
     if (lane < TC) {
@@ -902,8 +938,14 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         }
       }
     }
-    bulk_wait_all0();
-    fence_async_all();
+    // Another substep re-reads the stored rows through TMA: wait for the bulk stores to land and order the generic
+    // writes (pm_new, released particles) before them.  The last substep only needs the stores' shared-memory reads
+    // to be over (bulk_wait_read0 per tile); the writes complete with the kernel.
+    const bool more = sub + 1 < nsteps;
+    if (more) {
+      bulk_wait_all0();
+      fence_async_all();
+    }
     __syncthreads();
 
     WG_STAMP(t_p4);
@@ -998,7 +1040,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
               make_float4(sh.u[t], knu1_env, sh.cg[t], sh.sg[t]);
         }
       }
-      fence_async_all();
+      if (more) fence_async_all();
     }
     ++nstep;
     __syncthreads();
@@ -1038,6 +1080,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     d.load[bf] = sh.pre[T];
     if (a.mode == FLOW_STEP && f == 1) d.base_pow_mean[b] = sh.base_sum / (float)nsteps;
   }
+  WG_PHASE(6)  // after the tile loop: barrier wait, turbine epilogue, particle release, write-back
   if (warp == 0) {  // every warp's last TMEM access precedes the substep loop's closing barrier
     __syncwarp();
     tmem_dealloc(sh.tmem_base);
@@ -1059,6 +1102,18 @@ static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
 }
 
 #ifdef WG_TRACE
+extern "C" int wg_debug_phase_read(unsigned long long* out, int reset) {
+  static unsigned long long host[8 * 4 * 16384];
+  cudaError_t e = cudaMemcpyFromSymbol(host, g_phase, sizeof(host));
+  for (int k = 0; k < 8; ++k) out[k] = 0;
+  for (size_t i = 0; i < 8 * 4 * 16384; ++i) out[i & 7] += host[i];
+  if (reset) {
+    void* p = nullptr;
+    cudaGetSymbolAddress(&p, g_phase);
+    cudaMemset(p, 0, sizeof(host));
+  }
+  return (int)e;
+}
 extern "C" int wg_debug_trace_read(unsigned long long* out, int n_cta) {
   return (int)cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 8 * n_cta);
 }
