@@ -13,13 +13,16 @@ marks = sorted([("ptx helpers", 1), ("tmem helpers", find("TMEM scratch\n") if F
          ("flush_hits", find("struct RotorAcc")), ("prologue", find("__global__ void __launch_bounds__")),
          ("substep head (controller/retire/prefix)", find("for (int sub = 0; sub < nsteps")),
          ("tile pipeline (load/prefetch/store)", find("warp-private tile pipeline")),
-         ("bracket detection", find("// ---- superposition")), ("round end + turbine epilogue", find("    bulk_wait_all0();")),
+         ("bracket detection", find("// ---- superposition")), ("round end + turbine epilogue", find("const bool more = sub + 1 < nsteps;")),
          ("particle release", find("// release one particle per turbine")), ("tail", find("d.yaw[bf * T + tid] = sh.yaw[tid];"))], key=lambda m: m[1])
 agg = {}
 for l in out.splitlines()[1:]:
     parts = l.split()
     if len(parts) < 6: continue
-    f = parts[0].rstrip(":"); ln = int(parts[1]); i = float(parts[3].rstrip("%")); s = float(parts[5].rstrip("%"))
+    try:
+        f = parts[0].rstrip(":"); ln = int(parts[1]); i = float(parts[3].rstrip("%")); s = float(parts[5].rstrip("%"))
+    except ValueError:
+        continue
     g = "cuda headers (shuffles etc.)" if f != "flow.cu" else [m[0] for m in marks if m[1] <= ln][-1]
     a = agg.setdefault(g, [0.0, 0.0]); a[0] += i; a[1] += s
 print(out.splitlines()[0])

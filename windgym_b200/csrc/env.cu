@@ -9,33 +9,48 @@ namespace wg {
 // numpy's pairwise summation (contiguous float64, numpy/core/src/umath/loops_utils.h.src) so that window means
 // round exactly like the reference's np.mean on the same samples.
 template <class Get>
-__device__ double pairwise_sum(Get get, int lo, int n) {
+__device__ __forceinline__ double pairwise_block(Get get, int lo, int n) {  // n <= 128: numpy's unrolled-by-8 leaf
   if (n < 8) {
     double res = 0.0;
     for (int i = 0; i < n; ++i) res += get(lo + i);
     return res;
   }
-  if (n <= 128) {
-    double r[8];
+  double r[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r[k] = get(lo + k);
-    int i = 8;
-    for (; i < n - (n % 8); i += 8) {
+  for (int k = 0; k < 8; ++k) r[k] = get(lo + k);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r[k] += get(lo + i + k);
-    }
-    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-    for (; i < n; ++i) res += get(lo + i);
-    return res;
+    for (int k = 0; k < 8; ++k) r[k] += get(lo + i + k);
   }
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; ++i) res += get(lo + i);
+  return res;
+}
+template <class Get>
+__device__ __noinline__ double pairwise_split(Get get, int lo, int n) {  // n > 128: numpy halves the range
+  if (n <= 128) return pairwise_block(get, lo, n);
   int n2 = n / 2;
   n2 -= n2 % 8;
-  return pairwise_sum(get, lo, n2) + pairwise_sum(get, lo + n2, n - n2);
+  return pairwise_split(get, lo, n2) + pairwise_split(get, lo + n2, n - n2);
+}
+template <class Get>
+__device__ __forceinline__ double pairwise_sum(Get get, int lo, int n) {
+  return n <= 128 ? pairwise_block(get, lo, n) : pairwise_split(get, lo, n);
 }
 
 // 2*(val-lo)/(hi-lo)-1 evaluated in float32 exactly like numpy does on a float32 array (MesClass.py:324-326)
 __device__ __forceinline__ float scale_f32(float val, float lo, float span) {
   return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(val, lo)), span), 1.0f);
+}
+
+__device__ __forceinline__ void cp_async4(float* dst_shared, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst_shared, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_shared)), "l"(src)
+               : "memory");
 }
 
 __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   const int b = blockIdx.x * WG_FIN_WARPS + warp;
   if (b >= d.Bg) return;
   if (a.mask && !a.mask[b]) return;
-  extern __shared__ float s_dyn[];
+  extern __shared__ __align__(16) float s_dyn[];
   __shared__ float s_vals[WG_FIN_WARPS][4][WG_MAX_T];
   float (*s_val)[WG_MAX_T] = s_vals[warp];
   float* g_rings = d.rings + (size_t)b * d.ring_floats;
@@ -94,12 +109,21 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   float* rings = STAGE ? s_dyn + (size_t)warp * per_env : g_rings;
   float* fp = STAGE ? rings + d.ring_floats : g_fp;
   float* bp = STAGE ? fp + d.power_avg : g_bp;
-  if (STAGE) {
-    for (int i = lane; i < d.ring_floats; i += 32) rings[i] = g_rings[i];
-    for (int i = lane; i < d.power_avg; i += 32) { fp[i] = g_fp[i]; bp[i] = g_bp[i]; }
+  if (STAGE) {  // asynchronous copies (LDGSTS): every load of the env is in flight before the first wait
+    const bool v16 = ((d.ring_floats | per_env) & 3) == 0;  // rows 16-byte aligned in global and shared memory
+    if (v16) {
+      for (int i = lane * 4; i < d.ring_floats; i += 128) cp_async16(rings + i, g_rings + i);
+    } else {
+      for (int i = lane; i < d.ring_floats; i += 32) cp_async4(rings + i, g_rings + i);
+    }
+    for (int i = lane; i < d.power_avg; i += 32) { cp_async4(fp + i, g_fp + i); cp_async4(bp + i, g_bp + i); }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // scalars of the env, loaded up front (used by the pushes and the reward at the end)
   int np = d.n_push[b];
   int nfp_tot = d.n_fp[b], nbp_tot = d.n_bp[b];
+  const float g_base_pow = d.base_pow_mean[b], g_rated = d.rated[b];
+  const int g_ts = d.timestep[b], g_tmax = d.time_max[b];
   if (a.flags & (FIN_PUSH_MES | FIN_PUSH_FP))
     for (int t = lane; t < T; t += 32) {
       const float* src[4] = {a.in_ws, a.in_wd, a.in_yaw, a.in_power};
@@ -107,6 +131,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
       for (int c = 0; c < 4; ++c)
         s_val[c][t] = (a.flags & FIN_MEAS_FROM_ARGS) ? src[c][b * T + t] : d.meas[(b * 4 + c) * T + t];
     }
+  if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
 
   if (a.flags & FIN_PUSH_FP) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977): noise-free means
@@ -121,7 +146,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   }
   if (a.flags & FIN_PUSH_BP) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
     if (lane == 0) {
-      const float v = d.base_pow_mean[b];
+      const float v = g_base_pow;
       bp[nbp_tot % d.power_avg] = v;
       if (STAGE) g_bp[nbp_tot % d.power_avg] = v;
       d.n_bp[b] = nbp_tot + 1;
@@ -169,14 +194,16 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
           double acc = 0.0;
           for (int t = 0; t < T; ++t) {
             const float* rg = rings + d.ring_off[t];
-            auto get = [&](int k) { return (double)rg[(np - L + k) % H]; };
+            const int st = (np - L) % H;  // oldest sample of the deque; k < L <= H: one conditional wrap
+            auto get = [&](int k) { int i = st + k; if (i >= H) i -= H; return (double)rg[i]; };
             acc += (double)scale_f32(calc_ti(get, L), d.ti_lo, d.ti_span);
           }
           val = (float)(acc / T);
         } else {
           const int c = ds.chan, H = d.ch_H[c], L = min(np, H);
           const float* rg = rings + d.ring_off[ds.ring];
-          auto get = [&](int k) { return (double)rg[(np - L + k) % H]; };
+          const int st = (np - L) % H;
+          auto get = [&](int k) { int i = st + k; if (i >= H) i -= H; return (double)rg[i]; };
           float raw;
           if (ds.kind == 0) {
             raw = rg[(np - 1) % H];
@@ -207,7 +234,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     if (d.power_reward == 1) {
       rew = (sfp / nfp) / (sbp / nbp) - 1.0;
     } else if (d.power_reward == 2) {
-      rew = (sfp / nfp) / T / (double)d.rated[b];
+      rew = (sfp / nfp) / T / (double)g_rated;
     } else if (d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
       const int ws_ = PA / 10, ntot = nfp_tot;
       auto lg = [&](int k) { return (double)fp[(ntot - nfp + k) % PA]; };
@@ -228,8 +255,8 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
       rew -= (double)d.action_penalty * pen;
     }
     a.reward[b] = (float)rew;
-    const int ts = d.timestep[b];
-    a.truncated[b] = ts >= d.time_max[b] ? 1 : 0;  // Wind_Farm_Env.py:1003, :1027
+    const int ts = g_ts;
+    a.truncated[b] = ts >= g_tmax ? 1 : 0;  // Wind_Farm_Env.py:1003, :1027
     d.timestep[b] = ts + 1;
   }
 }
