@@ -130,6 +130,17 @@ int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, v
 int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
             void* cuda_stream);
 
+/* WindFarmEnv.step with HOST buffers -- the call a host-side user of the reference makes (numpy action in, numpy
+ * obs / reward / truncated out, Wind_Farm_Env.py:920-1034), in one entry point: copies actions_host (float32
+ * [n_active, T*act_var]; pinned memory for an asynchronous copy) into the caller's device staging buffer
+ * actions_dev, runs wg_step into the packed device result buffer out_dev, copies it to out_host and waits for the
+ * stream.  Packed result layout (caller-owned, both sides): obs f32 [B, obs] | reward f32 [B] | truncated u8 [B]
+ * with B = n_envs of the handle; out_bytes must equal that size (wg_result_bytes).  Unlike every other entry
+ * point this one synchronises the host with the stream before it returns. */
+int wg_result_bytes(const wg_handle* h, size_t* out);
+int wg_step_host(wg_handle* h, void* state, const float* actions_host, float* actions_dev, void* out_dev,
+                 void* out_host, size_t out_bytes, void* cuda_stream);
+
 /* DWMFlowSimulation.step()/run() alone (dynamiks seam, call sites Wind_Farm_Env.py:734,:745,:945): advance the
  * flow of every env by n_steps with the current yaws; no measurement bookkeeping. */
 int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream);

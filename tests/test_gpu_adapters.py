@@ -188,3 +188,29 @@ def test_pooled_autoreset_swaps_in_predeveloped_envs(built_lib):
     assert tiny.stats["swapped"] == 1 and tiny.stats["sync_resets"] == 2
     assert (tiny.state["timestep"].cpu().numpy() == 0).all() and np.isfinite(tiny.obs.cpu().numpy()).all()
     tiny.close()
+
+
+def test_step_host_equals_step(built_lib):
+    """Host-buffer step (numpy in, numpy out, one packed D2H copy) gives the same results as the device step."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    cfg = small_config(2, 2, reward="Power_avg", action="wind")
+    B, T = 6, 4
+    rng = np.random.default_rng(3)
+    ws = rng.uniform(7, 12, B); wd = rng.uniform(262, 278, B); ti = np.full(B, 0.07); yaw0 = rng.uniform(-15, 15, (B, T))
+    acts = rng.uniform(-1, 1, (5, B, T)).astype(np.float32)
+    a = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0")
+    b = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0")
+    a.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    b.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    pinned = torch.from_numpy(acts).pin_memory()
+    for k in range(5):
+        o, r, _, tr, _ = a.step(torch.as_tensor(acts[k]))
+        src = pinned[k] if k % 2 else acts[k]          # pinned tensor and pageable numpy array both work
+        oh, rh, th = b.step_host(src)
+        assert oh.dtype == np.float32 and rh.dtype == np.float32 and th.dtype == np.bool_
+        assert np.array_equal(oh, o.cpu().numpy()) and np.array_equal(rh, r.cpu().numpy())
+        assert np.array_equal(th, tr.cpu().numpy().astype(bool))
+    with pytest.raises(ValueError):
+        b.step_host(np.zeros((B, T + 1), dtype=np.float32))
+    a.close(); b.close()

@@ -62,6 +62,9 @@ SYMBOLS = {
     "wg_state_field_name": (C.c_char_p, [C.c_void_p, C.c_int32]),
     "wg_reset": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(ResetArgs), C.c_void_p, C.c_void_p]),
     "wg_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_result_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "wg_step_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
     "wg_flow_steps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_mes_push_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),

@@ -517,6 +517,36 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   return WG_OK;
 }
 
+int wg_result_bytes(const wg_handle* h, size_t* out) {
+  if (!h || !out) return fail(WG_ERR_INVALID, "wg_result_bytes: null argument");
+  const size_t B = (size_t)h->cfg.n_envs;
+  *out = B * (size_t)h->dev.obs_rows * (size_t)h->dev.obs_dim * 4 + B * 4 + B;
+  return WG_OK;
+}
+
+int wg_step_host(wg_handle* h, void* state, const float* actions_host, float* actions_dev, void* out_dev, void* out_host,
+                 size_t out_bytes, void* cuda_stream) {
+  if (!h || !state || !actions_host || !actions_dev || !out_dev || !out_host)
+    return fail(WG_ERR_INVALID, "wg_step_host: null argument");
+  size_t want = 0;
+  wg_result_bytes(h, &want);
+  if (out_bytes != want) return fail(WG_ERR_INVALID, "wg_step_host: out_bytes must equal wg_result_bytes");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  const size_t B = (size_t)h->cfg.n_envs;
+  const size_t act_bytes = (size_t)h->n_active * (size_t)h->cfg.n_turb * (size_t)h->dev.act_var * sizeof(float);
+  cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return cuda_fail(e, "wg_step_host: actions H2D");
+  unsigned char* o = reinterpret_cast<unsigned char*>(out_dev);
+  const size_t obs_bytes = B * (size_t)h->dev.obs_rows * (size_t)h->dev.obs_dim * 4;
+  const int rc = wg_step(h, state, actions_dev, reinterpret_cast<float*>(o), reinterpret_cast<float*>(o + obs_bytes),
+                         o + obs_bytes + B * 4, cuda_stream);
+  if (rc != WG_OK) return rc;
+  if ((e = cudaMemcpyAsync(out_host, out_dev, out_bytes, cudaMemcpyDeviceToHost, s)) != cudaSuccess)
+    return cuda_fail(e, "wg_step_host: results D2H");
+  if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return cuda_fail(e, "wg_step_host: cudaStreamSynchronize");
+  return WG_OK;
+}
+
 int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, int32_t nx, int32_t ny, int32_t nz,
                       float dx, float dy, float dz) {
   if (!h) return fail(WG_ERR_INVALID, "wg_set_turbulence: null argument");

@@ -64,9 +64,14 @@ class VecWindFarmEnv:
                 _lib.check(self.lib.wg_set_added_turbulence(self._h, _ptr(self.added_box.raw), nx, ny, nz,
                                                             *self.added_box.dxyz, 0.6, 0.35))
         self.obs_shape = (self.n_envs, self.n_turb, self.obs_var) if multi_agent else (self.n_envs, self.obs_var)
-        self.obs = torch.zeros(self.obs_shape, dtype=torch.float32, device=self.device)
-        self.reward = torch.zeros(self.n_envs, dtype=torch.float32, device=self.device)
-        self.truncated = torch.zeros(self.n_envs, dtype=torch.uint8, device=self.device)
+        # obs | reward | truncated live in ONE device buffer, so that a host caller gets a step's results with a
+        # single device-to-host copy (step_host)
+        n_obs = int(np.prod(self.obs_shape))
+        self._out = torch.zeros(n_obs * 4 + self.n_envs * 4 + self.n_envs, dtype=torch.uint8, device=self.device)
+        self.obs = self._out[:n_obs * 4].view(torch.float32).view(self.obs_shape)
+        self.reward = self._out[n_obs * 4:(n_obs + self.n_envs) * 4].view(torch.float32)
+        self.truncated = self._out[(n_obs + self.n_envs) * 4:]
+        self._host = None   # pinned host staging of step_host (allocated on first use)
         self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=self.device)
         self._step_ptrs = (_ptr(self._state), _ptr(self.obs), _ptr(self.reward), _ptr(self.truncated))
         # host copies of the per-env wind conditions of the current episode
@@ -325,6 +330,45 @@ class VecWindFarmEnv:
             _lib.check(rc)
         self._last_actions = actions
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
+
+    def step_host(self, actions):
+        """``step()`` for callers whose buffers live on the HOST (the reference's contract: numpy in, numpy out):
+        actions float32 [B, T*act_var] (numpy array or CPU tensor; pinned memory avoids a staging copy) are copied
+        to the device, the step runs, and obs / reward / truncated come back with ONE device-to-host copy into
+        pinned host memory.  Returns numpy views (obs [B,obs], reward [B], truncated bool [B]) that stay valid
+        until the next ``step_host`` call, after synchronising the stream; ``info`` stays on the device
+        (``self._info()``)."""
+        if self._host is None:
+            n_obs = int(np.prod(self.obs_shape))
+            res = torch.empty(self._out.numel(), dtype=torch.uint8).pin_memory()
+            act = torch.empty((self.n_envs, self.n_turb * self.ec.act_var), dtype=torch.float32).pin_memory()
+            self._host = {
+                "res": res, "act": act,
+                "act_dev": torch.empty(act.shape, dtype=torch.float32, device=self.device),
+                "obs": res[:n_obs * 4].view(torch.float32).view(self.obs_shape).numpy(),
+                "reward": res[n_obs * 4:(n_obs + self.n_envs) * 4].view(torch.float32).numpy(),
+                "truncated": res[(n_obs + self.n_envs) * 4:].numpy().view(np.bool_)}
+            nb = C.c_size_t()
+            _lib.check(self.lib.wg_result_bytes(self._h, C.byref(nb)))
+            assert nb.value == self._out.numel(), "packed result buffer does not match the library's layout"
+            self._host.update(act_ptr=_ptr(self._host["act_dev"]), out_ptr=_ptr(self._out),
+                              res_ptr=C.c_void_p(res.data_ptr()), n_res=C.c_size_t(nb.value))
+        h = self._host
+        n_act = getattr(self, "n_active", self.n_envs)
+        a = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
+        if a.numel() != n_act * self.n_turb * self.ec.act_var:
+            raise ValueError(f"actions must have {n_act}x{self.n_turb * self.ec.act_var} elements")
+        a = a.to(torch.float32).contiguous().reshape(n_act, -1)
+        if not a.is_pinned():           # pageable source: stage through the pinned buffer (one host memcpy)
+            h["act"][:n_act].copy_(a)
+            a = h["act"][:n_act]
+        # one C-ABI call: H2D of the actions, the two kernels, D2H of the packed results, stream synchronise
+        rc = self.lib.wg_step_host(self._h, self._step_ptrs[0], C.c_void_p(a.data_ptr()), h["act_ptr"], h["out_ptr"],
+                                   h["res_ptr"], h["n_res"], self._stream())
+        if rc != 0:
+            _lib.check(rc)
+        self._last_actions = h["act_dev"][:n_act]
+        return h["obs"], h["reward"], h["truncated"]
 
     def set_active(self, n_active):
         """``wg_set_active``: ``step()`` advances only envs [0, n_active); the other slots are a spare pool
