@@ -554,6 +554,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 #define WG_PHASE(k)
 #endif
   if (!((a.farm_mask >> f) & 1)) return;
+  // TMEM first: the SM starts the next CTA of a tcgen05-allocating kernel only after this one has given up its
+  // allocation permit (measured, scripts/micro/cta_launch.cu: starts on an SM are spaced by the time to the
+  // relinquish -- 0.5 us when it is the first instruction, 2.9 us behind the prologue's loads)
+  if (warp == 0) tmem_alloc(&sh.tmem_base);
   // ---- prologue: every global load of the CTA is issued before the first use of any of them (one round trip to
   // L2 / HBM instead of a chain of them: each dependent group costs 0.6 - 0.8 us while the CTA holds its slot)
   const bool is_t = tid < T;
@@ -580,9 +584,14 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     }
   }
   if (tab_mine) { g_tws = d.tab_ws[tid]; g_tp = d.tab_p[tid]; g_tct = d.tab_ct[tid]; }
-  if (!g_mask) return;
   const int nsteps = (a.mode == FLOW_FIXED) ? a.n_fixed : (a.mode == FLOW_SPIN ? g_spin : d.S);
-  if (nsteps <= 0) return;
+  if (!g_mask || nsteps <= 0) {  // nothing to do for this env (CTA-uniform): give the TMEM columns back
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) tmem_dealloc(sh.tmem_base);
+    return;
+  }
 
   const float dt = d.dt, R = d.R;
   const float rR = 1.f / R;
@@ -638,7 +647,6 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     sh.tab_ct[tid] = g_tct;
   }
   if (tid == 0) sh.base_sum = 0.f;
-  if (warp == 0) tmem_alloc(&sh.tmem_base);
   for (int i = T + tid; i < 2 * TC; i += blockDim.x) sh.xs[i] = CUDART_INF_F;
   if (lane == 0) {
     mbar_init(bar, 1);
