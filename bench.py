@@ -149,7 +149,7 @@ def _oracle_worker(args):
     return done, time.perf_counter() - t0
 
 
-def cpu_port_single(nx, ny, reward, budget_s=12.0, max_steps=400):
+def cpu_port_single(nx, ny, reward, budget_s=12.0, max_steps=4000):
     """Oracle port, one env on one core, bounded sample (reported beside the GPU number; not the target)."""
     done, dt = _oracle_worker((0, nx, ny, reward, max_steps, 3, False, budget_s))
     return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
@@ -362,6 +362,15 @@ def run_gpu(a):
         except Exception:
             pass
         achieved = bytes_flow / (t_flow_ms * 1e-3) / 1e9
+        # DRAM bytes of one launch from the committed `ncu --set full` capture of this exact workload (null otherwise)
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "flow_ncu_traffic.json")) as fh:
+                tr_ = json.load(fh)
+            if (tr_["nx"], tr_["ny"], tr_["envs"], tr_["reward"], tr_["turbtype"]) == (a.nx, a.ny, B, a.reward, a.turbtype):
+                traffic, traffic_src = tr_["dram_bytes_read"] + tr_["dram_bytes_write"], tr_["source"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": world * B * K / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -370,7 +379,8 @@ def run_gpu(a):
                     "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms / K_e2e},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "wg_flow_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "ms_per_launch": t_flow_ms, "finish_kernel_ms": fin_ms / max(n_prof, 1),
                          "live_stations_per_env_farm": live / (B * F), "bytes_per_station": STATION_BYTES,
                          "algorithmic_bytes_per_launch": bytes_flow, "launches_timed": int(n_prof)},

@@ -237,15 +237,15 @@ __device__ __forceinline__ void moved(const float4 pm, const float4 pc, float ws
 // Back substitution (pass C) writes the new profile and accumulates its bw.  Returns the new centre value.
 // With h = 1/(2j), N = nu/dr^2:
 //   lap_j dr^2 = U_{j+1} + U_{j-1} - 2 U_j + h (U_{j+1} - U_{j-1}),  Vd_j = nu Vh_j / (2 dr) = -N h I_j,
-//   sub-diagonal -a_j = -(N - N h (1 + I_j)), super-diagonal c_j = -N - N h (1 + I_j), diagonal U_j/dx + 2N.
+//   sub-diagonal -a_j = -(N - N h (1 + I_j)), super-diagonal c_j = -N - N h (1 + I_j), diagonal U_j/dx + 2N
+//   (the code multiplies each row by dx: diagonal U_j + 2 N dx, right-hand side U_j^2).
 // The sweep carries Z = h (1 + I) instead of I: with h_j j/2 = 1/4 and rho_j = h_{j+1}/h_j = j/(j+1),
 //   G_j = (lap_j dr^2 + h dU (I + rgh)) / den = ((su - 2 U_j) + dU Zp_j) / den,   Zp_j = h_j (1 + I_{j-1} + rgh_{j-1}),
 //   Z_j = Zp_j + G_j/4,  Zp_{j+1} = rho_j (Z_j + G_j/4),  a_j = N - N Z_j,  c_j = -N - N Z_j   (Zp_1 = 1/2),
 // so the only per-node grid constant is rho_j.
 #define WG_NODE_FWD(uj, up1, um, rho, AXIS)                                             \
   {                                                                                     \
-    const float ui = (uj) * idx;                                                        \
-    float bb = ui + N2, dd = ui * (uj), a = 0.f, cc = -2.f * N2;                        \
+    float bb = (uj) + N2, dd = (uj) * (uj), a = 0.f, cc = -2.f * N2;                    \
     if (AXIS) {                                                                         \
       bb += N2; /* axis node: diagonal U_0/dx + 4N, super-diagonal -4N, no sub-diagonal */ \
     } else {                                                                            \
@@ -273,8 +273,9 @@ __device__ __forceinline__ float march_row_tmem(uint32_t rowk, uint32_t taddr, f
   float4 nxt = lds4(rowk ^ 16u);
   const float bw = lds1((rowk ^ ((NC - 1) << 4)) + 12u);
   const float nu = knu1 * f1_filter(xt) + K2 * f2_filter(xt) * bw;
-  const float idx = 1.f / fmaxf(dxt, DXT_MIN);
-  const float N = nu * IDR2, N2 = 2.f * N;
+  // every row of the system is scaled by dx (Thomas' c', d' are invariant under row scaling): the diagonal is
+  // U_j + 2 N dx and the right-hand side U_j^2, with N = nu dx / dr^2 -- one multiplication per node less
+  const float N = nu * IDR2 * fmaxf(dxt, DXT_MIN), N2 = 2.f * N;
   float Zp = 0.5f, cpm = 0.f, dpm = 0.f, um = 0.f;
   {  // chunk 0
     const float uu[5] = {cur.x, cur.y, cur.z, cur.w, nxt.x};
