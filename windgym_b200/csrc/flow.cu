@@ -754,19 +754,21 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         pmc = __ldcg(reinterpret_cast<const float4*>(pm_old + st_c * 4u));
         pcc = __ldcg(reinterpret_cast<const float4*>(pcon + st_c * 4u));
       }
-      // age neighbours outside this tile (older = flat index - 1 of the same chain, younger = + 1): pull their
-      // scalars towards L2 now, they are loaded after the march
+      // age neighbours outside this tile (older = flat index - 1 of the same chain, younger = + 1): their scalars
+      // are loaded now, in flight together with the tile, and reduced to the moved position before the march (three
+      // registers across the march instead of a dependent load chain in front of the bracket search)
       const int ch_o = __shfl_up_sync(full, Lc.chain, 1), ch_y = __shfl_down_sync(full, Lc.chain, 1);
       const int vy_ = __shfl_down_sync(full, Lc.valid, 1);
       const bool has_o = Lc.valid && Lc.q > 0;
       const bool has_y = Lc.valid && Lc.q < sh.count[Lc.chain] - 1;
       const bool need_o = has_o && (lane == 0 || ch_o != Lc.chain);
       const bool need_y = has_y && (lane == 31 || !vy_ || ch_y != Lc.chain);
+      float4 pmx = make_float4(0.f, 0.f, 0.f, 0.f), pcx = pmx;
       if (need_o || need_y) {
         const int sx = need_o ? (Lc.slot == 0 ? P - 1 : Lc.slot - 1) : (Lc.slot == P - 1 ? 0 : Lc.slot + 1);
         const unsigned st_x = (unsigned)(Lc.chain * P + sx);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pm_old + st_x * 4u));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pcon + st_x * 4u));
+        pmx = __ldcg(reinterpret_cast<const float4*>(pm_old + st_x * 4u));
+        pcx = __ldcg(reinterpret_cast<const float4*>(pcon + st_x * 4u));
       }
       // while the tile is in flight: find the next tile and pull its rows and scalars towards L2
       if (tile + WG_NWARP < ntiles) {
@@ -789,6 +791,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       if (Lc.valid) {
         const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
         moved(pmc, pcc, ws, dt, tvc, xn, yn, zn, dx);
+      }
+      float xe = 0.f, ye = 0.f, ze = 0.f;  // moved position of the out-of-tile neighbour (the older one if both)
+      if (need_o || need_y) {
+        const float2 tvx = TURB ? sample_lp(d, pmx.x, pmx.y, pmx.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
+        float dxx;
+        moved(pmx, pcx, ws, dt, tvx, xe, ye, ze, dxx);
       }
       const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
@@ -818,16 +826,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       {
         float xo = __shfl_up_sync(full, xn, 1), yo = __shfl_up_sync(full, yn, 1), zo = __shfl_up_sync(full, zn, 1);
         float xy = __shfl_down_sync(full, xn, 1), yy = __shfl_down_sync(full, yn, 1), zy = __shfl_down_sync(full, zn, 1);
-        if (need_o || need_y) {  // one out-of-tile neighbour per lane (the older one if it needs both)
-          const unsigned sx = (unsigned)(Lc.chain * P + (need_o ? (Lc.slot == 0 ? P - 1 : Lc.slot - 1)
-                                                                : (Lc.slot == P - 1 ? 0 : Lc.slot + 1)));
-          const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
-          const float4 pc = __ldcg(reinterpret_cast<const float4*>(pcon + sx * 4u));
-          const float2 tvx = TURB ? sample_lp(d, pm.x, pm.y, pm.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
-          float dxx;
-          if (need_o) moved(pm, pc, ws, dt, tvx, xo, yo, zo, dxx);
-          else moved(pm, pc, ws, dt, tvx, xy, yy, zy, dxx);
-        }
+        if (need_o) { xo = xe; yo = ye; zo = ze; }  // one out-of-tile neighbour per lane (the older one if both)
+        else if (need_y) { xy = xe; yy = ye; zy = ze; }
         if (need_o && need_y) {  // rare: a one-station segment needs both neighbours from outside the tile
           const unsigned sx = (unsigned)(Lc.chain * P + (Lc.slot == P - 1 ? 0 : Lc.slot + 1));
           const float4 pm = __ldcg(reinterpret_cast<const float4*>(pm_old + sx * 4u));
