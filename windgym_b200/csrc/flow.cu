@@ -391,6 +391,16 @@ __device__ __forceinline__ int count_below(const float* xs, int top, float x) {
   return c;
 }
 
+// two independent searches in one loop (their shared-memory loads overlap)
+__device__ __forceinline__ void count_below2(const float* xs, int top, float x1, float x2, int& c1, int& c2) {
+  c1 = 0; c2 = 0;
+  for (int s = top; s > 0; s >>= 1) {
+    const float a = xs[c1 + s - 1], b = xs[c2 + s - 1];
+    if (a < x1) c1 += s;
+    if (b < x2) c2 += s;
+  }
+}
+
 struct LaneLoc {
   int chain, slot, q, valid;
 };
@@ -783,21 +793,31 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         }
       }
       const uint32_t rowk = row_a ^ ((uint32_t)(Lc.slot & 7) << 4);
-      WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches
+      // Everything that needs only the station scalars -- the move of this station and of its out-of-tile
+      // neighbour, their positions among the sorted rotor planes -- runs while the tile is still in flight.  With a
+      // turbulence box the moves wait for gathers that miss L2; there the block runs behind the tile wait (measured:
+      // 0.671 vs 0.693 ms per launch for the Mann variant).
+      float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
+      float xe = 0.f, ye = 0.f, ze = 0.f;  // moved position of the out-of-tile neighbour (the older one if both)
+      int cn = 0, ce = 0;  // #{rotor planes upstream of} this station / its out-of-tile neighbour, after the move
+      auto move_and_search = [&]() {
+        if (Lc.valid) {
+          const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
+          moved(pmc, pcc, ws, dt, tvc, xn, yn, zn, dx);
+        }
+        if (need_o || need_y) {
+          const float2 tvx = TURB ? sample_lp(d, pmx.x, pmx.y, pmx.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
+          float dxx;
+          moved(pmx, pcx, ws, dt, tvx, xe, ye, ze, dxx);
+        }
+        count_below2(sh.xs, xs_top, xn, xe, cn, ce);
+      };
+      if (!TURB) move_and_search();
+      WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches, moves, plane searches
       mbar_wait(bar, phase);
       phase ^= 1u;
       WG_PHASE(2)  // waiting for the tile
-      float xn = 0.f, yn = 0.f, zn = 0.f, dx = 0.f;
-      if (Lc.valid) {
-        const float2 tvc = TURB ? sample_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
-        moved(pmc, pcc, ws, dt, tvc, xn, yn, zn, dx);
-      }
-      float xe = 0.f, ye = 0.f, ze = 0.f;  // moved position of the out-of-tile neighbour (the older one if both)
-      if (need_o || need_y) {
-        const float2 tvx = TURB ? sample_lp(d, pmx.x, pmx.y, pmx.z, xs_t, tb_yo, tb_zo, tb_sc) : tv0;
-        float dxx;
-        moved(pmx, pcx, ws, dt, tvx, xe, ye, ze, dxx);
-      }
+      if (TURB) move_and_search();
       const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
@@ -841,12 +861,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         // neighbour), interval B = [younger neighbour, self (older end)); an inverted pair counts with sign -1
         // (oracle/dwm_numpy.py:353-356).  Every lane handles its own row for both of its intervals.  In-tile
         // neighbours pass their count by shuffle; the out-of-tile ones share one extra search.
-        const int cn = count_below(sh.xs, xs_top, xn);
         int co = __shfl_up_sync(full, cn, 1), cy = __shfl_down_sync(full, cn, 1);
-        if (__any_sync(full, need_o || need_y)) {
-          const int ce = count_below(sh.xs, xs_top, need_o ? xo : xy);
-          if (need_o) co = ce; else if (need_y) cy = ce;
-        }
+        if (need_o) co = ce; else if (need_y) cy = ce;
         if (__any_sync(full, need_o && need_y)) {
           const int ce = count_below(sh.xs, xs_top, xy);
           if (need_o && need_y) cy = ce;
