@@ -187,7 +187,7 @@ def run_reference(a):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -397,14 +397,36 @@ def run_gpu(a):
         line["config"]["n_passthrough"] = n_pass
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_port_single(a.nx, a.ny, a.reward)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def reserve_stdout():
+    """Keep the real stdout for the ONE JSON line: everything else that writes to fd 1 (NCCL's version banner, library
+    chatter) is sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
