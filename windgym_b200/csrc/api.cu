@@ -131,6 +131,7 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.wd = at<float>(state, h, "wd");
   d.rated = at<float>(state, h, "rated_power");
   d.xmax = at<float>(state, h, "xmax");
+  d.knu1 = at<float>(state, h, "knu1");
   d.k_emit = at<int>(state, h, "k_emit");
   d.time_max = at<int>(state, h, "time_max");
   d.timestep = at<int>(state, h, "timestep");
@@ -344,7 +345,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "n_step", 1, {B, F});
   add_field(h, "load", 1, {B, F});
   for (const char* n : {"yaw", "u", "v", "w", "power", "ct", "derate"}) add_field(h, n, 0, {B, F, T});
-  for (const char* n : {"ws", "ti", "wd", "rated_power", "xmax", "base_pow_mean"}) add_field(h, n, 0, {B});
+  for (const char* n : {"ws", "ti", "wd", "rated_power", "xmax", "knu1", "base_pow_mean"}) add_field(h, n, 0, {B});
   for (const char* n : {"k_emit", "time_max", "timestep", "flags", "n_push", "n_fp", "n_bp", "spin"})
     add_field(h, n, 1, {B});
   add_field(h, "xr", 0, {B, T});

@@ -301,6 +301,7 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
     for (int t = 0; t < T; ++t) xm = fmax(xm, (d.x_pos[t] - mx) * c + (d.y_pos[t] - my) * s);
     d.xmax[b] = (float)xm;
     d.ws[b] = a.ws[b]; d.ti[b] = a.ti[b]; d.wd[b] = a.wd[b]; d.rated[b] = a.rated[b];
+    d.knu1[b] = a.ti[b] > 0.f ? K1 * powf(a.ti[b], 0.3f) : 0.f;
     d.k_emit[b] = a.k_emit[b]; d.time_max[b] = a.time_max[b]; d.spin[b] = a.t_dev[b];
     d.timestep[b] = 0; d.n_push[b] = 0; d.flags[b] = 0; d.base_pow_mean[b] = 0.f;
     for (int k = 0; k < 3; ++k) d.tb_off[b * 3 + k] = a.tb_off ? a.tb_off[b * 3 + k] : 0.f;

@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // wg_step launches the envs longest first (a.order): the CTAs that drain the grid are then the short ones
-  const int bi = blockIdx.x / F, f = blockIdx.x % F;
+  const int bi = F == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, f = F == 2 ? (int)(blockIdx.x & 1) : 0;  // F is 1 or 2
   const int b = a.order ? a.order[bi] : bi;
   const int bf = b * F + f;
 #ifdef WG_TRACE
@@ -578,7 +578,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   const bool tab_mine = tab_sh && tid < d.n_tab;  // tables of up to 32 knots: one knot per thread
   const uint8_t g_mask = a.mask ? a.mask[b] : (uint8_t)1;
   const int g_spin = a.mode == FLOW_SPIN ? d.spin[b] : 0;
-  const float ws = d.ws[b], wd = d.wd[b], xmax = d.xmax[b], ti = d.ti[b];
+  const float ws = d.ws[b], wd = d.wd[b], xmax = d.xmax[b];
+  const float knu1_env = d.knu1[b];  // K1 TI^0.3 of the episode (ambient term of the eddy viscosity), set at reset
   const int g_kemit = d.k_emit[b];
   int nstep = d.n_step[bf];
   float g_xr = 0.f, g_yr = 0.f, g_xs = 0.f, g_yaw = 0.f, g_der = 1.f, g_u = 0.f, g_v = 0.f, g_w = 0.f, g_pw = 0.f, g_ct = 0.f;
@@ -606,7 +607,6 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 
   const float dt = d.dt, R = d.R;
   const float rR = 1.f / R;
-  const float knu1_env = ti > 0.f ? K1 * powf(ti, 0.3f) : 0.f;
   const int k_emit = max(g_kemit, 1);
   float* __restrict__ prof = d.prof + (size_t)bf * T * P * WG_NR;
   float* __restrict__ pcon = d.pcon + (size_t)bf * T * P * 4;

@@ -77,6 +77,7 @@ struct Dev {
   float *derate;          // [B,F,T] induction scale delta in [derate_min, 1] (1 = the reference's turbine)
   // env state
   float *ws, *ti, *wd, *rated, *xmax;   // [B]
+  float *knu1;            // [B] K1 TI^0.3: ambient-turbulence term of the eddy viscosity (emission scalar of new particles)
   int *k_emit, *time_max, *timestep, *flags, *n_push, *n_fp, *n_bp, *spin;  // [B]
   float *xr, *yr;         // [B,T]
   float *xs_sorted;       // [B,T] rotor-plane x ascending (ties by turbine index); int *ord_sorted: turbine of each
