@@ -81,6 +81,8 @@ def test_null_arguments(built_lib):
     assert built_lib.wg_state_bytes(None, C.byref(n)) == -1
     assert built_lib.wg_step(None, None, None, None, None, None, None) == -1
     assert built_lib.wg_profile_enable(None, 1) == -1
+    assert built_lib.wg_result_bytes(None, C.byref(n)) == -1
+    assert built_lib.wg_step_host(None, None, None, None, None, None, 0, None) == -1
     assert "null argument" in built_lib.wg_last_error().decode()
 
 
