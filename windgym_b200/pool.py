@@ -28,13 +28,18 @@ class PooledVecEnv:
         if len(v.obs_shape) != 2:
             raise ValueError("PooledVecEnv wraps the single-agent observation layout")
         v.set_active(self.n_envs)
-        self.refill_chunk = int(refill_chunk) if refill_chunk is not None else max(1, self.reserve // 2)
+        # Spares are recycled in batches of reserve/4 right after a step has been launched (the host side of a masked
+        # reset -- condition draws, argument upload, ~50 launches -- then overlaps with the GPU stepping the active
+        # envs), on a ring of background streams: one spin-up is ~300 serial flow steps, i.e. tens of ms whatever the
+        # batch size, so the supply of ready spares is (envs in preparation) / latency and refills must overlap.
+        self.refill_chunk = int(refill_chunk) if refill_chunk is not None else max(1, self.reserve // 4)
         self.device, self.ec, self.n_turb, self.obs_var = v.device, v.ec, v.n_turb, v.obs_var
         self.obs_shape = (self.n_envs, v.obs_var)
         self.Baseline_comp, self.n_farms = v.Baseline_comp, v.n_farms
         self.yaw_min, self.yaw_max, self.yaw_step = v.yaw_min, v.yaw_max, v.yaw_step
         self.x_pos, self.y_pos = v.x_pos, v.y_pos
-        self._bg = torch.cuda.Stream(device=self.device)
+        self._bgs = [torch.cuda.Stream(device=self.device) for _ in range(4)]
+        self._bg_next = 0
         self._ready, self._refilling, self._free = [], [], []      # [(slot, event)], [(slots, event, keep)], [slot]
         self.stats = {"swapped": 0, "sync_resets": 0, "refills": 0}
         B = self.n_envs
@@ -88,8 +93,13 @@ class PooledVecEnv:
 
     def _info(self):
         B = self.n_envs
-        return {k: (v[:B] if hasattr(v, "shape") and len(v.shape) and v.shape[0] == B + self.reserve else v)
-                for k, v in self.inner._info().items()}
+        d = getattr(self, "_info_views", None)
+        if d is None:   # device views are live: slice them once, refresh only the host-side wind conditions
+            d = {k: (v[:B] if hasattr(v, "shape") and len(v.shape) and v.shape[0] == B + self.reserve else v)
+                 for k, v in self.inner._info().items()}
+            self._info_views = d
+        d["Wind speed Global"], d["Wind direction Global"], d["Turbulence intensity"] = self.ws, self.wd, self.ti
+        return dict(d)
 
     def close(self):
         torch.cuda.synchronize(self.device)
@@ -120,6 +130,9 @@ class PooledVecEnv:
 
     def step(self, actions):
         obs, rew, term, trunc, _ = self.inner.step(actions)
+        if len(self._free) >= self.refill_chunk:                   # behind the launch: see refill_chunk
+            self._refill(self._free)
+            self._free = []
         B = self.n_envs
         return obs[:B], rew[:B], term[:B], trunc[:B], self._info()
 
@@ -133,22 +146,26 @@ class PooledVecEnv:
         done_reading.record(main)                                   # copies out of these slots are ordered before
         m = np.zeros(self.n_envs + self.reserve, dtype=bool)
         m[slots] = True
-        with torch.cuda.stream(self._bg):
-            self._bg.wait_event(done_reading)
+        bg = self._bgs[self._bg_next]
+        self._bg_next = (self._bg_next + 1) % len(self._bgs)
+        with torch.cuda.stream(bg):
+            bg.wait_event(done_reading)
             self.inner.reset(mask=m)
             keep = self.inner._keep
             ev = torch.cuda.Event()
-            ev.record(self._bg)
+            ev.record(bg)
         self._refilling.append((list(slots), ev, keep))
         self.stats["refills"] += 1
 
     def _collect(self, block=False):
-        """Move finished background batches to the ready list (``block``: take the oldest one even if unfinished --
-        the main stream then waits for it on the device, the host does not)."""
-        while self._refilling and (self._refilling[0][1].query() or block):
-            slots, ev, _ = self._refilling.pop(0)
-            self._ready += [(s, ev) for s in slots]
-            block = False
+        """Move finished background batches to the ready list (``block``: if none has finished take the oldest one
+        anyway -- the main stream then waits for it on the device, the host does not)."""
+        done = [r for r in self._refilling if r[1].query()]
+        if not done and block and self._refilling:
+            done = [self._refilling[0]]
+        for r in done:
+            self._refilling.remove(r)
+            self._ready += [(s, r[1]) for s in r[0]]
 
     def _swap_in(self, idx):
         self._collect()
@@ -169,6 +186,3 @@ class PooledVecEnv:
             m[idx[take:]] = True
             self.inner.reset(mask=m)
             self.stats["sync_resets"] += len(idx) - take
-        if len(self._free) >= self.refill_chunk:
-            self._refill(self._free)
-            self._free = []

@@ -281,7 +281,12 @@ class VecWindFarmEnv:
         if yaw0 is not None:
             y0[sel] = np.broadcast_to(np.asarray(yaw0, dtype=np.float64), (B, T))[sel]
         self.ws, self.ti, self.wd = ws, ti, wd
-        n_spin, time_max, k_emit = ec.reset_integers(ws, wd)
+        # integer decisions of the reset, for the selected envs only (the kernel ignores the others)
+        n_spin, k_emit = np.zeros(B, dtype=np.int32), np.ones(B, dtype=np.int32)
+        prev_tm = getattr(self, "time_max", None)
+        time_max = np.zeros(B, dtype=np.int32) if prev_tm is None or len(prev_tm) != B else np.array(prev_tm, dtype=np.int32)
+        if sel.size:
+            n_spin[sel], time_max[sel], k_emit[sel] = ec.reset_integers(ws[sel], wd[sel])
         rated = np.asarray(self.turbine.power(ws), dtype=np.float64)
         ti_flow = np.zeros(B)  # turbtype "None": RandomTurbulence(ti=0) (Wind_Farm_Env.py:661-665)
         tb = {}
@@ -377,16 +382,36 @@ class VecWindFarmEnv:
         self.n_active = int(n_active)
 
     def copy_envs(self, src, dst):
-        """``wg_copy_envs``: complete per-env state of slot src[k] -> slot dst[k] (device copy on the current stream)."""
-        s = torch.as_tensor(np.asarray(src, dtype=np.int32)).to(self.device)
-        t = torch.as_tensor(np.asarray(dst, dtype=np.int32)).to(self.device)
-        _lib.check(self.lib.wg_copy_envs(self._h, _ptr(self._state), _ptr(s), _ptr(t), int(s.numel()), self._stream()))
-        self._keep_copy = (s, t)
-        self.obs[t.long()] = self.obs[s.long()]
+        """``wg_copy_envs``: complete per-env state of slot src[k] -> slot dst[k] (device copy on the current stream).
+        The index lists go through one pinned staging buffer and one H2D copy; the observation rows follow."""
+        src = np.asarray(src, dtype=np.int64).reshape(-1)
+        dst = np.asarray(dst, dtype=np.int64).reshape(-1)
+        n = int(src.size)
+        if n == 0:
+            return
+        st = getattr(self, "_swap_stage", None)
+        if st is None or st["cap"] < n:
+            cap = max(64, 2 * n)
+            st = {"cap": cap, "host": torch.empty(2 * cap, dtype=torch.int32).pin_memory(),
+                  "dev": torch.empty(2 * cap, dtype=torch.int32, device=self.device), "ev": None}
+            st["np"] = st["host"].numpy()
+            self._swap_stage = st
+        if st["ev"] is not None:
+            st["ev"].synchronize()           # the previous lists have been read (normally long ago)
+        st["np"][:n] = src
+        st["np"][n:2 * n] = dst
+        dev = st["dev"][:2 * n]
+        dev.copy_(st["host"][:2 * n], non_blocking=True)
+        st["ev"] = torch.cuda.Event()
+        st["ev"].record(torch.cuda.current_stream(self.device))
+        _lib.check(self.lib.wg_copy_envs(self._h, _ptr(self._state), C.c_void_p(dev.data_ptr()),
+                                         C.c_void_p(dev.data_ptr() + 4 * n), n, self._stream()))
+        idx = dev.long()
+        self.obs.index_copy_(0, idx[n:], self.obs.index_select(0, idx[:n]))
         for arr in (self.ws, self.ti, self.wd, self.time_max):
-            arr[np.asarray(dst)] = arr[np.asarray(src)]
+            arr[dst] = arr[src]
         if getattr(self, "turb_box", None) is not None:
-            self.turb_offset[np.asarray(dst)] = self.turb_offset[np.asarray(src)]
+            self.turb_offset[dst] = self.turb_offset[src]
 
     def flow_steps(self, n):
         """DWMFlowSimulation.run(n*dt) for every env and farm, without measurement bookkeeping."""
