@@ -166,3 +166,37 @@ def test_flow_state_matches_oracle_particles(built_lib):
             bw = np.sqrt(np.maximum(2.0 * M * (1.0 - U.min(axis=1)), 0.0))
             assert np.allclose(env.last_bw, bw, atol=2e-5), "shear integral carried in the Dirichlet slot"
         assert np.allclose(env.state["u"][b, 0].cpu().numpy(), fs.rotor_avg_windspeed[:, 0], rtol=2e-5)
+
+
+def test_launch_order_and_retire_bookkeeping(built_lib, monkeypatch):
+    """wg_step launches the envs longest first (state field `order`): the order is a permutation of the active envs
+    sorted by live stations, and -- envs being independent -- results are bit-identical to the plain index order.
+    `retire` (stations the next step drops) never exceeds `count`, and dropped stations lie beyond the farm."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    cfg = small_config(3, 2, reward="Power_avg", action="wind")
+    B, T = 96, 6
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=11)
+    acts = np.random.default_rng(5).uniform(-1, 1, (70, B, T)).astype(np.float32)   # > 64 steps: one periodic rebuild
+    # the order is built from the loads the previous flow launch left behind: check it on the first step after a reset
+    env_0 = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0")
+    env_0.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    load0 = env_0.state["load"].cpu().numpy().sum(axis=1)
+    env_0.step(torch.as_tensor(acts[0]))
+    order = env_0.state["order"].cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(B)), "order must be a permutation of the active envs"
+    quantum = max(1, -(-(env_0.n_farms * T * env_0.ec.p_cap) // 1024))
+    key = np.minimum(load0[order] // quantum, 1023)
+    assert len(set(load0.tolist())) > 8 and np.all(np.diff(key) <= 0), "envs must be launched by descending load class"
+    env_0.close()
+    env_a, out_a = _run_gpu(cfg, ws, ti, wd, yaw0, acts)
+    assert np.array_equal(np.sort(env_a.state["order"].cpu().numpy()), np.arange(B))
+    count, retire = env_a.state["count"].cpu().numpy(), env_a.state["retire"].cpu().numpy()
+    assert (retire >= 0).all() and (retire <= count).all() and (retire <= 8).all()
+    assert retire.sum() > 0 or count.sum() > 0
+    env_a.close()
+    monkeypatch.setenv("WG_NO_ORDER", "1")          # read at wg_create
+    env_b, out_b = _run_gpu(cfg, ws, ti, wd, yaw0, acts)
+    env_b.close()
+    for k in ("obs", "reward", "power", "yaw", "trunc"):
+        assert np.array_equal(out_a[k], out_b[k]), f"{k} depends on the launch order"
