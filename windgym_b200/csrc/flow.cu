@@ -4,16 +4,20 @@
 // One CTA (4 warps) owns one (env, farm).  Its live wake stations (all turbine chains, ring-addressed) form one
 // flat list that the CTA's warps stream in 32-station tiles:
 //     cp.async.bulk (TMA 1-D bulk copy, mbarrier complete_tx)  HBM -> shared
+//     while the tile is in flight: station scalars (own + the one age neighbour outside the tile), the move of the
+//       wake centres, their positions among the sorted rotor planes, L2 prefetch of the next tile
 //     thread-per-station implicit Ainslie march: ONE fused forward sweep (continuity-consistent radial
 //       velocity + tridiagonal rows + Thomas elimination; d' written in place into the shared row, c' parked in
 //       the thread's own TMEM lane with tcgen05.st) and one back substitution (tcgen05.ld) that also accumulates
 //       the shear-layer integrals of the NEW profile for the next step's eddy viscosity
-//     rotor-plane bracket detection (per-lane binary search over the sorted rotor planes) -> per-warp hit list
+//     rotor-plane bracket detection (plane index ranges from the searches above; hits whose wake cannot reach the
+//       rotor are dropped: exact zeros) -> per-warp hit list
 //       -> (hit x quadrature point) mapped onto full warps, 16-lane shuffle reduction for the rotor average,
 //       per-rotor partial sums in registers                                             (superposition gather)
 //     cp.async.bulk shared -> HBM
 // then the per-turbine epilogue (P/CT tables, particle release) runs in the same CTA, and the substep loop
-// (dt_env/dt_sim, or a whole spin-up) repeats without leaving the kernel.
+// (dt_env/dt_sim, or a whole spin-up) repeats without leaving the kernel.  wg_step launches the envs longest first
+// (FlowArgs::order); the stations a step retires were found by the lanes that marched them in the previous one.
 // Algorithmic traffic per station and step: 256 B profile + 16 B mutable + 16 B emission scalars read,
 // 256 B + 16 B written = 560 B.  HBM/issue bound; no tensor cores (stencil + gather).
 //
