@@ -189,6 +189,9 @@ void build_desc(const wg_config& cfg, std::vector<wg::ObsDesc>& out, int& obs_di
     }
     emit_chan(v, 3, 3 * T + t, m.turb_power, lo[3], hi[3]);
   };
+  auto fill_channel = [&](std::vector<wg::ObsDesc>& v) {
+    for (auto& d : v) { d.H = ch[d.chan]->history_length; d.N = ch[d.chan]->history_N; d.W = ch[d.chan]->window_length; }
+  };
   const int fr = 4 * T;  // farm rings: ws, wd, power
   if (!m.multi_agent) {
     for (int t = 0; t < T; ++t) turb_block(out, t);
@@ -200,6 +203,7 @@ void build_desc(const wg_config& cfg, std::vector<wg::ObsDesc>& out, int& obs_di
       out.push_back(d);
     }
     emit_chan(out, 3, fr + 2, m.farm_power, lo[3], hi[3] * T);
+    fill_channel(out);
     obs_rows = 1;
     obs_dim = (int)out.size();
   } else {
@@ -218,6 +222,7 @@ void build_desc(const wg_config& cfg, std::vector<wg::ObsDesc>& out, int& obs_di
       turb_block(out, t);
       out.insert(out.end(), farm.begin(), farm.end());
     }
+    fill_channel(out);
     obs_rows = T;
     obs_dim = (int)out.size() / T;
   }

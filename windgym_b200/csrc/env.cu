@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long splitmix(unsigned long long x) {
   x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
   return x ^ (x >> 31);
 }
-__device__ float normal_noise(unsigned long long seed, int b, int push, int chan, int t) {
+__device__ __noinline__ float normal_noise(unsigned long long seed, int b, int push, int chan, int t) {
   unsigned long long k = splitmix(seed ^ splitmix(((unsigned long long)b << 32) ^ (unsigned)push));
   k = splitmix(k ^ (((unsigned long long)chan << 32) | (unsigned)t));
   unsigned long long k2 = splitmix(k);
@@ -80,7 +80,7 @@ __device__ __forceinline__ void window_bounds(int L, int N, int W, int i, int& l
 
 // np.std(u - U) / U over a whole ring (turb_mes.calc_TI, MesClass.py:220-237), float64 like the reference
 template <class Get>
-__device__ float calc_ti(Get get, int L) {
+__device__ __noinline__ float calc_ti(Get get, int L) {  // rare observation kind: kept out of the hot path's code
   double U = pairwise_sum(get, 0, L) / L;
   auto dev = [&](int k) { return get(k) - U; };
   double m2 = pairwise_sum(dev, 0, L) / L;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
           }
           val = (float)(acc / T);
         } else {
-          const int c = ds.chan, H = d.ch_H[c], L = min(np, H);
+          const int H = ds.H, L = min(np, H);
           const float* rg = rings + d.ring_off[ds.ring];
           const int st = (np - L) % H;
           auto get = [&](int k) { int i = st + k; if (i >= H) i -= H; return (double)rg[i]; };
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
             raw = rg[(np - 1) % H];
           } else if (ds.kind == 1) {
             int lo, hi;
-            window_bounds(L, d.ch_N[c], d.ch_W[c], ds.win, lo, hi);
+            window_bounds(L, ds.N, ds.W, ds.win, lo, hi);
             raw = (float)(pairwise_sum(get, lo, hi - lo) / (hi - lo));
           } else {
             raw = calc_ti(get, L);

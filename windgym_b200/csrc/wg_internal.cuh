@@ -38,6 +38,8 @@ struct ObsDesc {
   int32_t chan;   // 0 ws, 1 wd, 2 yaw, 3 power
   int32_t win;    // window index i (kind 1)
   float lo, span; // scaling: 2*(v-lo)/span-1, span = float32(double(hi)-double(lo))
+  int32_t H, N, W; // history_length / history_N / window_length of the channel (copied here: no dynamic indexing
+                   // of the kernel-parameter arrays in the observation loop)
 };
 
 struct Dev {
