@@ -336,6 +336,9 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
     d.noise_std[c] = cfg->mes.noise_std[c];
   }
   d.noise = cfg->mes.noise; d.noise_seed = cfg->mes.noise_seed;
+  bool ti_obs = false;
+  for (const auto& od : desc) ti_obs |= od.kind >= 2;
+  d.fin_lean = (!cfg->mes.noise && !ti_obs && cfg->power_reward != 3) ? 1 : 0;
   d.ti_lo = (float)cfg->mes.ti_min; d.ti_span = (float)(cfg->mes.ti_max - cfg->mes.ti_min);
   d.ring_off = h->d_ring_off; d.ring_chan = h->d_ring_chan; d.obs_desc = h->d_desc;
   d.tab_ws = h->d_tab_ws; d.tab_p = h->d_tab_p; d.tab_ct = h->d_tab_ct; d.x_pos = h->d_x; d.y_pos = h->d_y;

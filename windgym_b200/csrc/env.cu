@@ -93,7 +93,10 @@ __device__ __noinline__ float calc_ti(Get get, int L) {  // rare observation kin
 // STAGE = true: the env's measurement rings and power deques are staged in shared memory first (one coalesced
 // read instead of dependent global loads inside the serial window sums); pushes go to both copies.
 #define WG_FIN_WARPS 4
-template <bool STAGE>
+// LEAN = true: the common configuration -- no measurement noise, no TI observations, no Power_diff reward -- compiled
+// without those paths (a third of the code: this 20 us single-wave kernel pays for every instruction line it has
+// to fetch cold); the host picks the variant from the handle's configuration.
+template <bool STAGE, bool LEAN>
 __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const Dev d, const FinishArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
   const int b = blockIdx.x * WG_FIN_WARPS + warp;
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float v = s_val[c][t];
-        if (d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, t);
+        if (!LEAN && d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, t);
         s_val[c][t] = v;
         const int r = c * T + t;
         const int o = d.ring_off[r] + np % d.ch_H[c];
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
       const ObsDesc ds = d.obs_desc[o];
       float val = 0.f;
       if (np > 0) {
-        if (ds.kind == 3) {  // farm TI = mean of the (individually scaled) turbine TIs (MesClass.py:670-673)
+        if (!LEAN && ds.kind == 3) {  // farm TI = mean of the (individually scaled) turbine TIs (MesClass.py:670-673)
           const int H = d.ch_H[0], L = min(np, H);
           double acc = 0.0;
           for (int t = 0; t < T; ++t) {
@@ -207,7 +210,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
           float raw;
           if (ds.kind == 0) {
             raw = rg[(np - 1) % H];
-          } else if (ds.kind == 1) {
+          } else if (LEAN || ds.kind == 1) {
             int lo, hi;
             window_bounds(L, ds.N, ds.W, ds.win, lo, hi);
             raw = (float)(pairwise_sum(get, lo, hi - lo) / (hi - lo));
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
       rew = (sfp / nfp) / (sbp / nbp) - 1.0;
     } else if (d.power_reward == 2) {
       rew = (sfp / nfp) / T / (double)g_rated;
-    } else if (d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
+    } else if (!LEAN && d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
       const int ws_ = PA / 10, ntot = nfp_tot;
       auto lg = [&](int k) { return (double)fp[(ntot - nfp + k) % PA]; };
       double latest = 0.0, oldest = 0.0;
@@ -316,13 +319,16 @@ cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
   if (smem <= 100 * 1024) {
     static size_t configured = 0;
     if (smem > 48 * 1024 && smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(wg_finish_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       configured = smem;
     }
-    wg_finish_kernel<true><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
+    if (d.fin_lean) wg_finish_kernel<true, true><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
+    else wg_finish_kernel<true, false><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
   } else {
-    wg_finish_kernel<false><<<grid, WG_FIN_WARPS * 32, 0, s>>>(d, a);
+    wg_finish_kernel<false, false><<<grid, WG_FIN_WARPS * 32, 0, s>>>(d, a);
   }
   return cudaGetLastError();
 }

@@ -57,6 +57,7 @@ struct Dev {
   int n_rings, ring_floats, obs_dim, obs_rows;  // obs_rows = 1 (single agent) or T (multi agent)
   int ch_cur[4], ch_roll[4], ch_N[4], ch_H[4], ch_W[4];
   int noise;
+  int fin_lean;           // no noise, no TI observations, no Power_diff reward: the lean finish-kernel variant applies
   float noise_std[4];
   unsigned long long noise_seed;
   float ti_lo, ti_span;
