@@ -118,3 +118,29 @@ def test_p_cap_never_overflows_for_any_direction():
         assert ec.p_cap * min_spacing >= diag + 2 * ec.D
     assert EnvConfig(small_config(4, 4), V80()).p_cap == 168
     assert EnvConfig(rich_config(8, 8), V80()).p_cap % 8 == 0
+
+
+def test_fast_rng_replicates_numpy_streams():
+    """windgym_b200.fast_rng evaluates default_rng([seed, env, episode]) for many envs with array arithmetic: bit for
+    bit the same doubles as numpy's SeedSequence + PCG64, and sample_conditions gives identical draws on either path."""
+    from types import SimpleNamespace
+    from windgym_b200.fast_rng import uniform_streams
+    from windgym_b200.vec_env import VecWindFarmEnv
+    rng = np.random.default_rng(0)
+    for seed, ep in [(0, 0), (7, 3), (2 ** 32 - 1, 2 ** 32 - 1), (123456789, 41)]:
+        envs = np.concatenate([np.arange(40), rng.integers(0, 2 ** 32, 40)])
+        ref = np.array([np.random.default_rng([seed, int(i), ep]).random(11) for i in envs])
+        assert np.array_equal(uniform_streams(seed, envs, ep, 11), ref)
+    with pytest.raises(ValueError):
+        uniform_streams(2 ** 32, [0], 0, 1)
+    B, T = 64, 5
+    ec = SimpleNamespace(ws_min=7, ws_max=15.5, TI_min=0.02, TI_max=0.15, wd_min=255, wd_max=285.0, turbtype="None",
+                         yaw_init_mode="Random", yaw_start=15)
+    out = []
+    for no_fast in (False, True):
+        stub = SimpleNamespace(ec=ec, n_envs=B, n_turb=T, ws=np.zeros(B), ti=np.zeros(B), wd=np.zeros(B), _episode=2,
+                               sample_site=None, _wind_override={}, yaw_initial=None, _no_fast_rng=no_fast)
+        out.append(VecWindFarmEnv.sample_conditions(stub, 11, range(3, 60)))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    assert out[0][0][3] != 0 and out[0][0][0] == 0 and np.abs(out[0][3][10]).max() <= 15

@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .fast_rng import uniform_streams
 from .config import EnvConfig, load_yaml
 
 _TORCH_DT = {0: torch.float32, 1: torch.int32}
@@ -221,6 +222,20 @@ class VecWindFarmEnv:
             self._tf_seed = np.zeros(B, dtype=np.int64)
         ws, ti, wd = self.ws.copy(), self.ti.copy(), self.wd.copy()
         yaw0 = np.zeros((B, T))
+        # Many envs at once: the same bit streams evaluated with array arithmetic (windgym_b200/fast_rng.py, pinned
+        # against numpy in tests/test_host_logic.py) instead of one Generator object per env (17 us each).
+        idx = np.fromiter(envs, dtype=np.int64)
+        if (seed is not None and not (B == 1 and self._episode == 0) and self.sample_site is None
+                and ec.turbtype != "MannGenerate" and 0 <= int(seed) < 2 ** 32 and idx.size > 8
+                and not getattr(self, "_no_fast_rng", False)):
+            n_yaw = T if ec.yaw_init_mode == "Random" else 0
+            u = uniform_streams(int(seed), idx, self._episode, 3 + n_yaw)
+            ws[idx] = ec.ws_min + (ec.ws_max - ec.ws_min) * u[:, 0]      # Generator.uniform: low + (high - low) * u
+            ti[idx] = ec.TI_min + (ec.TI_max - ec.TI_min) * u[:, 1]
+            wd[idx] = ec.wd_min + (ec.wd_max - ec.wd_min) * u[:, 2]
+            if n_yaw:
+                yaw0[idx] = -ec.yaw_start + (ec.yaw_start - (-ec.yaw_start)) * u[:, 3:]
+            envs = ()
         for i in envs:
             if seed is None:
                 rng = np.random.default_rng()
@@ -245,13 +260,13 @@ class VecWindFarmEnv:
                 yaw0[i] = rng.uniform(low=-ec.yaw_start, high=ec.yaw_start, size=T)
         for k, arr in (("ws", ws), ("ti", ti), ("wd", wd)):
             if k in self._wind_override:
-                arr[list(envs)] = self._wind_override[k][list(envs)]
+                arr[idx] = self._wind_override[k][idx]
         if ec.yaw_init_mode == "Defined":
             yv = np.asarray(self.yaw_initial, dtype=np.float64)
             if yv.size not in (1, T):
                 raise ValueError("So I am pretty sure something has gone wrong here. The specified yaw values "
                                  "are not the right length.")
-            yaw0[list(envs)] = yv if yv.size == T else np.ones(T) * yv.reshape(-1)[0]
+            yaw0[idx] = yv if yv.size == T else np.ones(T) * yv.reshape(-1)[0]
         return ws, ti, wd, yaw0
 
     def _site(self):
