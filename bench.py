@@ -6,8 +6,9 @@
 
 One "step" = one batched ``VecWindFarmEnv.step`` over all envs of the rank: yaw update, S flow substeps of every
 farm (wake advection + Ainslie march + superposition + rotor average + turbine update), MesClass push/extract,
-reward, truncation.  Workload = BASELINE.json configs[1]: 16-turbine 4x4 grid, 4096 envs per GPU, yaw-only actions,
-Env1.yaml observation/yaw semantics, uniform inflow (turbtype "None"), synthetic U(-1,1) actions.
+reward, truncation.  Workload = BASELINE.json configs[1]: 16-turbine 4x4 grid, 4096 envs, yaw-only actions,
+Env1.yaml observation/yaw semantics, uniform inflow (turbtype "None"), synthetic U(-1,1) actions.  Under torchrun
+the 4096 envs are SHARDED over the ranks (strong scaling: BASELINE.json configs[2] = 512 per GPU at N = 8).
 Prints ONE JSON line on rank 0 (contract: see the task statement / DESIGN.md section "Measurement").
 """
 import argparse
@@ -177,10 +178,12 @@ def run_reference(a):
     value = sum(d / t for d, t in res)
     t_step = max(t for _, t in res) / a.steps
     sample = (f"{cores} envs (one per host core, envs 0..{cores - 1} of the workload) x {a.steps} steps after reset + "
-              f"{a.warmup} warm-up steps; whole run {wall:.1f} s")
+              f"{a.warmup} warm-up steps; whole run {wall:.1f} s; oracle PORT (oracle/env_numpy.py over "
+              "oracle/dwm_numpy.py): the unmodified reference env layer over the same restated solver runs within 5 % of "
+              "it (12.30 vs 12.89 ms/step on this workload, profiles/r05_reference_layer_vs_port.txt)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(a, cores, "cpu"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -191,20 +194,153 @@ def run_reference(a):
     return 0
 
 
-def bench_config(a, envs_per_rank, where):
-    return {"workload": f"BASELINE.json configs[1]: {a.nx * a.ny}-turbine {a.nx}x{a.ny} grid (V80, reference linspace "
-                        f"layout), {envs_per_rank} envs per {'GPU' if where == 'gpu' else 'step (one per host core)'}, "
-                        "yaw-only actions U(-1,1), Env1.yaml obs/yaw semantics, " +
+def bench_config(a, envs_per_rank, where, world=1):
+    total = envs_per_rank * world
+    return {"workload": f"BASELINE.json configs[{1 if world == 1 else 2}]: {a.nx * a.ny}-turbine {a.nx}x{a.ny} grid (V80, "
+                        f"reference linspace layout), " +
+                        (f"{total} envs total, {envs_per_rank} per GPU x {world} GPU(s)" if where == "gpu" else
+                         f"{envs_per_rank} envs per step (one per host core)") +
+                        ", yaw-only actions U(-1,1), Env1.yaml obs/yaw semantics, " +
                         ("turbtype None (uniform inflow)" if getattr(a, "turbtype", "None") == "None" else
-                         "Mann turbulence box 1024x128x32 @ 3 m shared by the envs"),
-            "n_turb": a.nx * a.ny, "envs_per_gpu": envs_per_rank if where == "gpu" else None,
+                         "Mann turbulence box shared by the envs"),
+            "n_turb": a.nx * a.ny, "envs_total": total if where == "gpu" else None,
+            "envs_per_gpu": envs_per_rank if where == "gpu" else None,
             "farms_per_env": 2 if a.reward == "Baseline" else 1, "power_reward": a.reward,
             "dt_env": 1, "dt_sim": 1, "obs_dim": 2 * a.nx * a.ny, "parallelism": f"env-sharded x{a.gpus}",
             "turbtype": getattr(a, "turbtype", "None"),
-            "l2_policy": "working set (wake state, GBs per step) exceeds the 126 MB L2; no explicit flush"}
+            "l2_policy": "working set (wake state, >= 200 MB per step and GPU) exceeds the 126 MB L2; no explicit flush"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def measure(torch, dist, env, acts_host, K, W, K_e2e, K_prof, world, extra_bytes_per_station=0):
+    """One workload on this rank's env: W warm-up + K device-timed steps (actions resident in HBM), then K_e2e steps
+    through step_host (host buffers in and out, synchronised every step), then K_prof steps with the library's own
+    CUDA events around each kernel.  Times are the max over ranks; station counts are summed over ranks."""
+    dev, B = env.device, env.n_envs
+    acts_dev = acts_host[:W + K].to(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(W):
+        env.step(acts_dev[i])
+    barrier()
+    l0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        env.step(acts_dev[i])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = env.launch_count - l0
+    t_ms = e0.elapsed_time(e1)
+    barrier()
+    env.check_flags()
+
+    # end to end through the public API with HOST buffers (VecWindFarmEnv.step_host -> C-ABI wg_step_host): the
+    # actions come from pinned host memory and obs | reward | truncated are back in host memory, the call returns
+    # when they are -- every step
+    base = W + K
+    for i in range(3):
+        obs_h, rew_h, tr_h = env.step_host(acts_host[base + i])
+    base += 3
+    barrier()
+    t0 = time.perf_counter()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    any_trunc = False
+    for i in range(K_e2e):
+        obs_h, rew_h, tr_h = env.step_host(acts_host[base + i])   # host in, host out, synchronised
+        any_trunc |= bool(tr_h.any())                             # the caller reads the result every step
+    e3.record()
+    torch.cuda.synchronize()
+    t_e2e_ms = max(e2.elapsed_time(e3), (time.perf_counter() - t0) * 1e3)
+    base += K_e2e
+    h2d = int(acts_host[0].numel()) * 4
+    d2h = obs_h.size * 4 + B * 4 + B
+    assert not any_trunc and not bool(tr_h.any()), "an env truncated inside the timed window"
+
+    # dominant kernel alone: CUDA events recorded by the library on the launching stream around each kernel
+    env.profile_enable(True)
+    acts_p = acts_host[base:base + K_prof].to(dev)
+    torch.cuda.synchronize()
+    for i in range(K_prof):
+        env.step(acts_p[i])
+    flow_ms, fin_ms, n_prof = env.profile_read()
+    env.profile_enable(False)
+    # live wake stations (all envs, farms, chains): the ring counts minus the stations the next step drops
+    live = int(env.state["count"].sum().item()) - int(env.state["retire"].sum().item())
+    env.check_flags()
+    F, S, T = env.n_farms, env.ec.S, env.n_turb
+    tt = torch.tensor([t_ms, t_e2e_ms, flow_ms / max(n_prof, 1), fin_ms / max(n_prof, 1)], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([live, B], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    t_ms, t_e2e_ms, t_flow_ms, t_fin_ms = [float(x) for x in tt.tolist()]
+    live_all, B_all = [float(x) for x in cnt.tolist()]
+    # algorithmic bytes of one flow launch, summed over the ranks (SURVEY.md 8(d)); per GPU = / world
+    bytes_flow = S * (live_all * (STATION_BYTES + extra_bytes_per_station) + B_all * F * T * TURB_BYTES)
+    peak, peak_src = hbm_peak()
+    achieved = bytes_flow / world / (t_flow_ms * 1e-3) / 1e9
+    return {
+        "value": B_all * K / (t_ms * 1e-3), "ms_per_step": t_ms / K, "launches": int(launches),
+        "e2e": {"value": B_all * K_e2e / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms / K_e2e},
+        "roofline": {"kernel": "wg_flow_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "ms_per_launch": t_flow_ms,
+                     "finish_kernel_ms": t_fin_ms, "live_stations_per_env_farm": live_all / (B_all * F),
+                     "bytes_per_station": STATION_BYTES + extra_bytes_per_station,
+                     "algorithmic_bytes_per_launch_per_gpu": bytes_flow / world, "launches_timed": int(n_prof),
+                     "per": "GPU (bytes of all ranks / n_gpus / max-over-ranks launch time)"},
+    }
+
+
+def make_env(torch, dev, rank, B, nx, ny, reward, total_steps, seed_base=0, **kw):
+    """A VecWindFarmEnv of this rank's B envs (global env ids rank*B ...), reset with the workload's conditions."""
+    from windgym_b200 import V80, VecWindFarmEnv
+    cfg = workload_config(nx, ny, reward)
+    n_pass = n_passthrough_for(total_steps, cfg)
+    env_ids = np.arange(rank * B, (rank + 1) * B)
+    ws, ti, wd, yaw0 = sample_conditions(cfg, env_ids, nx * ny, seed0=seed_base)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device=str(dev), n_passthrough=max(n_pass, kw.pop("n_passthrough", 0)),
+                         seed=rank, **kw)
+    env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    torch.cuda.synchronize()
+    assert int(np.min(env.time_max)) > total_steps, "episode would truncate inside the run"
+    return env, cfg, n_pass
+
+
+def side_leg(torch, dist, dev, rank, world, name, B, nx, ny, K, W, what, act_mult=1, extra_bytes_per_station=0, **kw):
+    """A secondary configuration measured with the same procedure as the headline one (fewer steps)."""
+    K_prof = min(K, 32)
+    n_act = W + K + 3 + K + K_prof
+    env, cfg, _ = make_env(torch, dev, rank, B, nx, ny, "Power_avg", n_act + 8, **kw)
+    gen = torch.Generator(device="cpu").manual_seed(4321 + rank)
+    acts = (torch.rand((n_act, B, nx * ny * act_mult), generator=gen, dtype=torch.float32) * 2 - 1).pin_memory()
+    m = measure(torch, dist, env, acts, K, W, K, K_prof, world, extra_bytes_per_station)
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    r = m["roofline"]
+    return {"what": what, "envs_per_gpu": B, "envs_total": B * world, "n_turb": nx * ny, "steps": K,
+            "value": m["value"], "unit": UNIT, "ms_per_step": m["ms_per_step"], "e2e": m["e2e"]["value"],
+            "e2e_ms_per_step": m["e2e"]["ms_per_step"], "roofline_frac": r["frac"], "achieved_gbs": r["achieved"],
+            "ms_per_launch": r["ms_per_launch"], "finish_kernel_ms": r["finish_kernel_ms"],
+            "live_stations_per_env_farm": r["live_stations_per_env_farm"], "bytes_per_station": r["bytes_per_station"]}
+
+
 def run_gpu(a):
     import torch
     import torch.distributed as dist
@@ -230,103 +366,46 @@ def run_gpu(a):
         g.build()
     if world > 1:
         dist.barrier()
-    from windgym_b200 import V80, VecWindFarmEnv
+    from windgym_b200 import V80
 
-    B, T, K, W = a.envs, a.nx * a.ny, a.steps, a.warmup
-    K_e2e = K
-    K_prof = min(K, 64)
-    total = W + K + 3 + K_e2e + K_prof + 8
-    cfg = workload_config(a.nx, a.ny, a.reward)
-    n_pass = n_passthrough_for(total, cfg)
-    env_ids = np.arange(rank * B, (rank + 1) * B)
-    ws, ti, wd, yaw0 = sample_conditions(cfg, env_ids, T)
-    kw = {}
-    if a.turbtype == "Mann":   # ambient turbulence: the reference tests' reduced box (tests/test_basics.py:38-45)
-        from windgym_b200.mann import MannBox
-        kw = dict(turbtype="MannFixed", turb_box=MannBox.generate(0.1, 33.6, 3.9, Nxyz=(1024, 128, 32), dxyz=(3.0, 3.0, 3.0),
-                                                                  seed=1234, device=str(dev)))
-    env = VecWindFarmEnv(V80(), B, config=cfg, device=str(dev), n_passthrough=n_pass, seed=rank, **kw)
-    env.reset(wind=(ws, ti, wd), yaw0=yaw0)
-    torch.cuda.synchronize()
-    assert int(np.min(env.time_max)) > total, "episode would truncate inside the run"
-
-    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
+    # STRONG scaling (BASELINE.json metric: "4096 envs at 1/2/4/8 B200"; configs[2]: 512 per GPU at 8): the batch of
+    # --envs-total envs is sharded over the ranks.  --envs pins the per-GPU count instead (weak scaling).
+    scaling = "strong"
+    if a.envs is not None:
+        B, scaling = a.envs, ("weak" if world > 1 else "strong")
+    else:
+        if a.envs_total % world:
+            raise SystemExit(f"--envs-total {a.envs_total} is not divisible by {world} ranks")
+        B = a.envs_total // world
+    T, K, W = a.nx * a.ny, a.steps, a.warmup
+    K_e2e, K_prof = K, min(K, 64)
     n_act = W + K + 3 + K_e2e + K_prof
+    kw = {}
+    extra_b = 0
+    if a.turbtype == "Mann":   # ambient turbulence + wake-added turbulence: MannFixed (Wind_Farm_Env.py:646-656)
+        kw, extra_b = mann_kwargs(dev, a.mann_box), MANN_GATHER_BYTES
+    env, cfg, n_pass = make_env(torch, dev, rank, B, a.nx, a.ny, a.reward, n_act + 8, **kw)
+    gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     acts_host = (torch.rand((n_act, B, T), generator=gen, dtype=torch.float32) * 2 - 1).pin_memory()
     acts_dev = acts_host[:W + K].to(dev)
-    torch.cuda.synchronize()
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    m = measure(torch, dist, env, acts_host, K, W, K_e2e, K_prof, world, extra_b)
+    clk = clocks.stop() if clocks else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up, then K timed steps with the inputs resident in HBM
-    for i in range(W):
-        env.step(acts_dev[i])
-    barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
-    l0 = env.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(W, W + K):
-        env.step(acts_dev[i])
-    e1.record()
-    torch.cuda.synchronize()
-    launches = env.launch_count - l0
-    t_ms = e0.elapsed_time(e1)
-    barrier()
-    env.check_flags()
-
-    # ---- end to end through the public API with HOST buffers (VecWindFarmEnv.step_host): pinned actions H2D, the
-    # step, obs | reward | truncated D2H (one copy of the packed result buffer), stream synchronised -- every step
-    base = W + K
-    for i in range(3):
-        obs_h, rew_h, tr_h = env.step_host(acts_host[base + i])
-    base += 3
-    barrier()
-    t0 = time.perf_counter()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    any_trunc = False
-    for i in range(K_e2e):
-        obs_h, rew_h, tr_h = env.step_host(acts_host[base + i])   # host in, host out, synchronised
-        any_trunc |= bool(tr_h.any())                             # the caller reads the result every step
-    e3.record()
-    torch.cuda.synchronize()
-    t_e2e_wall = (time.perf_counter() - t0) * 1e3
-    t_e2e_ms = max(e2.elapsed_time(e3), t_e2e_wall)
-    clk = clocks.stop() if clocks else None
-    base += K_e2e
-    h2d = B * T * 4
-    d2h = obs_h.size * 4 + B * 4 + B
-    assert not any_trunc and not bool(tr_h.any()), "an env truncated inside the timed window"
-
-    # ---- dominant kernel alone: CUDA events recorded by the library on the launching stream around each kernel
-    env.profile_enable(True)
-    acts_p = acts_host[base:base + K_prof].to(dev)
-    torch.cuda.synchronize()
-    for i in range(K_prof):
-        env.step(acts_p[i])
-    flow_ms, fin_ms, n_prof = env.profile_read()
-    env.profile_enable(False)
-    # live wake stations of this rank (all envs, farms, chains): the ring counts minus the stations the next step drops
-    live = int(env.state["count"].sum().item()) - int(env.state["retire"].sum().item())
-    F, S = env.n_farms, env.ec.S
-    # with a turbulence box every station also gathers 8 corners x 8 B of the low-pass box (not counted as
-    # algorithmic state traffic: the box is shared and L2-resident at this size)
-    bytes_flow = S * (live * STATION_BYTES + B * F * T * TURB_BYTES)
-    t_flow = flow_ms / max(n_prof, 1) * 1e-3
-    env.check_flags()
-
     # ---- SURVEY 8(d) metric (ii): throughput WITH auto-reset (episodes of the reference's length, n_passthrough = 5,
     # envs at random phases of their episodes, finished envs replaced from the spare pool, spin-up in the background)
     auto = None
+    env.close(); del env
+    torch.cuda.empty_cache()
     if not a.no_autoreset:
         from windgym_b200 import PooledVecEnv
         from windgym_b200.vector import GymVectorEnv
-        env.close(); del env
-        torch.cuda.empty_cache()
         K_ar = max(K, 200)
         pool = PooledVecEnv(V80(), B, reserve=max(64, B // 8), config=cfg, device=str(dev), n_passthrough=5, seed=rank, **kw)
         genv = GymVectorEnv(venv=pool, as_torch=True)
@@ -346,22 +425,42 @@ def run_gpu(a):
         pool.check_flags()
         auto = {"ms": t_ar, "steps": K_ar, "resets": n_res, "stats": dict(pool.stats), "reserve": pool.reserve}
         pool.close()
+        del genv, pool
+        torch.cuda.empty_cache()
+        ta = torch.tensor([auto["ms"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        auto["ms"] = float(ta.item())
 
-    # ---- max over ranks
-    tt = torch.tensor([t_ms, t_e2e_ms, t_flow * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_ms, t_e2e_ms, t_flow_ms = [float(x) for x in tt.tolist()]
+    # ---- the other BASELINE.json configurations, same procedure, fewer steps (driver-visible: "configs")
+    extra = {}
+    if not a.no_extras:
+        Ks, Ws = max(20, min(K, 40)), 5
+        if world == 1:
+            extra["cfg3_share_512_envs_1gpu"] = side_leg(
+                torch, dist, dev, rank, world, "cfg3", 512, 4, 4, Ks, Ws,
+                "one GPU's share of configs[2] (4096 envs sharded 512/GPU over 8 GPUs): 512 envs x 4x4 farm on 1 GPU")
+            extra["cfg4_8x8_1024_envs_yaw_induction"] = side_leg(
+                torch, dist, dev, rank, world, "cfg4", 1024, 8, 8, Ks, Ws,
+                "configs[3]: 64-turbine 8x8 farm, 1024 envs, yaw + induction actions (act_var = 2 extension)",
+                act_mult=2, induction_control=True)
+            extra["cfg2_mann"] = side_leg(
+                torch, dist, dev, rank, world, "mann", 4096, 4, 4, Ks, Ws,
+                "configs[1] with turbtype MannFixed: ambient Mann box + wake-added turbulence (meandering wakes); bytes "
+                "per station include the 8-corner gather of the low-pass box", extra_bytes_per_station=MANN_GATHER_BYTES,
+                **mann_kwargs(dev, a.mann_box))
+        if 2048 % world == 0:
+            extra["cfg5_multi_agent_4x2_2048_envs"] = side_leg(
+                torch, dist, dev, rank, world, "cfg5", 2048 // world, 4, 2, Ks, Ws,
+                f"configs[4]: WindFarmEnvMulti 8-turbine 4x2 farm, 2048 envs total ({2048 // world} per GPU x {world}), "
+                "per-agent observation rows obs f32[B, 8, 2]", multi_agent=True, n_passthrough=20)
+        if world > 1 and not a.no_weak:
+            extra["weak_scaling_4096_envs_per_gpu"] = side_leg(
+                torch, dist, dev, rank, world, "weak", 4096, 4, 4, Ks, Ws,
+                f"weak scaling: 4096 envs PER GPU ({4096 * world} envs total); not the BASELINE metric")
 
     if rank == 0:
-        peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
-        try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-                mp_ = json.load(fh)
-            peak, peak_src = float(mp_["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        except Exception:
-            pass
-        achieved = bytes_flow / (t_flow_ms * 1e-3) / 1e9
+        r = m["roofline"]
         # DRAM bytes of one launch from the committed `ncu --set full` capture of this exact workload (null otherwise)
         traffic, traffic_src = None, None
         try:
@@ -371,29 +470,22 @@ def run_gpu(a):
                 traffic, traffic_src = tr_["dram_bytes_read"] + tr_["dram_bytes_write"], tr_["source"]
         except Exception:
             pass
+        r["traffic"], r["traffic_source"] = traffic, traffic_src
         line = {
-            "metric": METRIC, "value": world * B * K / (t_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": t_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": bench_config(a, B, "gpu"),
-            "e2e": {"value": world * B * K_e2e / (t_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": t_e2e_ms / K_e2e},
-            "gpu_launches": int(launches),
-            "roofline": {"kernel": "wg_flow_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                         "traffic_source": traffic_src,
-                         "ms_per_launch": t_flow_ms, "finish_kernel_ms": fin_ms / max(n_prof, 1),
-                         "live_stations_per_env_farm": live / (B * F), "bytes_per_station": STATION_BYTES,
-                         "algorithmic_bytes_per_launch": bytes_flow, "launches_timed": int(n_prof)},
-            "clocks": clk,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench_config(a, B, "gpu", world),
+            "e2e": m["e2e"], "gpu_launches": m["launches"], "roofline": r, "clocks": clk,
         }
-        if auto is not None:   # rank 0's share, whole-job value extrapolated over the ranks (no cross-rank coupling)
+        if auto is not None:
             line["with_autoreset"] = {
                 "value": world * B * auto["steps"] / (auto["ms"] * 1e-3), "unit": UNIT, "ms_per_step": auto["ms"] / auto["steps"],
-                "steps": auto["steps"], "episodes_finished": auto["resets"], "spare_envs": auto["reserve"],
+                "steps": auto["steps"], "episodes_finished_rank0": auto["resets"], "spare_envs": auto["reserve"],
                 "pool": auto["stats"],
                 "what": "steady-state training loop: n_passthrough=5 episodes at random phases, finished envs swapped for "
-                        "pre-developed spares (spin-up batched on a background stream), truncation flags read on the host "
-                        "every step (wall clock)"}
+                        "pre-developed spares (spin-up batched on background streams); wall clock, max over ranks"}
+        if extra:
+            line["configs"] = extra
         line["config"]["n_passthrough"] = n_pass
         if world == 1 and not a.no_cpu:
             line["cpu_baseline"] = cpu_port_single(a.nx, a.ny, a.reward)
@@ -402,6 +494,18 @@ def run_gpu(a):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+MANN_GATHER_BYTES = 8 * 8   # low-pass box: 8 corners x float2 per station and step (random 32-byte sector reads)
+
+
+def mann_kwargs(dev, size):
+    """turbtype MannFixed.  size 'ref': the reference's box 2048 x 512 x 64 @ 3 m (Wind_Farm_Env.py:646-656);
+    'test': the reduced box of the reference's tests, 1024 x 128 x 32 (tests/test_basics.py:38-45)."""
+    from windgym_b200.mann import MannBox
+    nxyz = (2048, 512, 64) if size == "ref" else (1024, 128, 32)
+    return dict(turbtype="MannFixed", turb_box=MannBox.generate(0.1, 33.6, 3.9, Nxyz=nxyz, dxyz=(3.0, 3.0, 3.0), seed=1234,
+                                                                device=str(dev)))
 
 
 _JSON_FD = None
@@ -432,7 +536,11 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--envs-total", type=int, default=4096, help="envs of the whole job, sharded over the GPUs (strong scaling)")
+    ap.add_argument("--envs", type=int, default=None, help="envs PER GPU (overrides --envs-total; weak scaling under torchrun)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations (configs key)")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the weak-scaling leg (4096 envs per GPU)")
+    ap.add_argument("--mann-box", default="ref", choices=["ref", "test"], help="Mann box size of --turbtype Mann / cfg2_mann")
     ap.add_argument("--nx", type=int, default=4)
     ap.add_argument("--ny", type=int, default=4)
     ap.add_argument("--reward", default="Power_avg", choices=["Power_avg", "Baseline"],

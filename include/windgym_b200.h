@@ -131,12 +131,16 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
             void* cuda_stream);
 
 /* WindFarmEnv.step with HOST buffers -- the call a host-side user of the reference makes (numpy action in, numpy
- * obs / reward / truncated out, Wind_Farm_Env.py:920-1034), in one entry point: copies actions_host (float32
- * [n_active, T*act_var]; pinned memory for an asynchronous copy) into the caller's device staging buffer
- * actions_dev, runs wg_step into the packed device result buffer out_dev, copies it to out_host and waits for the
- * stream.  Packed result layout (caller-owned, both sides): obs f32 [B, obs] | reward f32 [B] | truncated u8 [B]
- * with B = n_envs of the handle; out_bytes must equal that size (wg_result_bytes).  Unlike every other entry
- * point this one synchronises the host with the stream before it returns. */
+ * obs / reward / truncated out, Wind_Farm_Env.py:920-1034), in one entry point.  actions_host: float32
+ * [n_active, T*act_var]; out_host: packed results obs f32 [B, obs] | reward f32 [B] | truncated u8 [B] with
+ * B = n_envs of the handle, out_bytes = wg_result_bytes.  actions_dev / out_dev: caller-owned device buffers of the
+ * same sizes (out_dev always receives the results too: device-side consumers keep working).
+ *  - both host buffers pinned (cudaHostAlloc / cudaHostRegister, e.g. torch pin_memory()): ZERO-COPY -- the flow
+ *    kernel reads the actions from the mapped host buffer, the finish kernel stores the results into out_host and
+ *    publishes the step's sequence number in a mapped word the call polls; no copy engine, no stream synchronise;
+ *  - pageable buffers: H2D copy into actions_dev, wg_step, D2H copy of out_dev, cudaStreamSynchronize.
+ * Either way the call returns when out_host holds the step's results (the only entry point besides
+ * wg_profile_read that waits for the device). */
 int wg_result_bytes(const wg_handle* h, size_t* out);
 int wg_step_host(wg_handle* h, void* state, const float* actions_host, float* actions_dev, void* out_dev,
                  void* out_host, size_t out_bytes, void* cuda_stream);

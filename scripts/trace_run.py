@@ -39,22 +39,27 @@ def main():
                         "move + march", "store issue + superposition", "wait for the store to release the buffer",
                         "after the tile loop (barrier, epilogue, release, write-back)"), phb):
         print(f"  warp time: {name:55s} {float(v) / tot * 100:5.1f} %")
-    n = B * env.n_farms
+    n = max(B * env.n_farms * 2, 2048)          # CTAs of the launch: one per work-table entry (parts of split farms)
     buf = np.zeros((n, 8), dtype=np.uint64)
     rc = lib.wg_debug_trace_read(buf.ctypes.data_as(C.c_void_p), C.c_int(n))
     assert rc == 0, rc
+    buf = buf[buf[:, 1] > 0]                     # unused table entries never stamp
+    n = len(buf)
     t0 = buf[:, 0].astype(np.int64); t1 = buf[:, 1].astype(np.int64)
-    sm = buf[:, 2].astype(np.int64); envb = (buf[:, 3] >> np.uint64(32)).astype(np.int64)
+    sm = (buf[:, 2] & np.uint64(0xffff)).astype(np.int64)
+    nparts = ((buf[:, 2] >> np.uint64(16)) & np.uint64(0xff)).astype(np.int64)
+    envb = (buf[:, 3] >> np.uint64(32)).astype(np.int64)
     nst = (buf[:, 3] & np.uint64(0xffffffff)).astype(np.int64)
     ph = buf[:, 4:8].astype(np.int64)
-    np.savez(out, t0=t0, t1=t1, sm=sm, env=envb, stations=nst, phases=ph)
+    np.savez(out, t0=t0, t1=t1, sm=sm, env=envb, stations=nst, phases=ph, nparts=nparts)
     seg = np.stack([ph[:, 0] - t0, ph[:, 1] - ph[:, 0], ph[:, 2] - ph[:, 1], ph[:, 3] - ph[:, 2], t1 - ph[:, 3]], 1) / 1e3
     for name, col in zip(("prologue (to first barrier)", "substep head (retire, prefix)", "tile loop (warp 0)",
                           "loop end -> epilogue barrier", "turbine epilogue + release + write-back"), seg.T):
         print(f"  {name:42s} mean {col.mean():6.2f} us  p10 {np.percentile(col, 10):6.2f}  p90 {np.percentile(col, 90):6.2f}")
     base = t0.min(); span = t1.max() - base
     dur = (t1 - t0) / 1e3
-    tiles = np.ceil(nst / 32); rounds = np.ceil(tiles / 4)
+    tiles = np.ceil(nst / 32); rounds = np.maximum(np.ceil(tiles / (4 * np.maximum(nparts, 1))), 1)
+    print(f"{n} CTAs; parts per farm: " + ", ".join(f"{k}: {int((nparts == k).sum())} CTAs" for k in np.unique(nparts)))
     print(f"kernel span {span / 1e3:.1f} us; CTA duration mean {dur.mean():.1f} us min {dur.min():.1f} max {dur.max():.1f}")
     A = np.vstack([rounds, np.ones_like(rounds)]).T
     coef, *_ = np.linalg.lstsq(A, dur, rcond=None)

@@ -19,3 +19,18 @@ def built_lib():
     g.build()
     from windgym_b200 import _lib
     return _lib.load()
+
+
+def pytest_collection_modifyitems(config, items):
+    """CPU-only machines: skip (not fail) everything marked ``gpu`` when no CUDA device is visible."""
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA B200 device (run through gpurun)")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)

@@ -13,6 +13,9 @@ see oracle/dwm_numpy.py).
 Files (all small):
   mes_golden.npz   farm_mes.add_measurements / get_measurements(scaled=True) on seeded random histories
   env_golden.npz   WindFarmEnv / FarmEval reset + step trajectories on the shipped YAMLs and variants
+  multi_golden.npz WindFarmEnvMulti (WindEnvMulti.py) reset + step: per-agent observation split, shared reward,
+                   half-length truncation
+  cfg1_golden.npz  BASELINE.json configs[0]: shipped 2turb.yaml, seed 1, 200 steps (zero action, then +0.5)
 """
 import json
 import os
@@ -176,15 +179,115 @@ def make_env(ns, out):
     out["meta"] = np.array(json.dumps(meta))
 
 
+def multi_cases():
+    """WindFarmEnvMulti cases: BASELINE.json cfg 5's shape (4x2 farm, Env1-style channels: 2 observations per agent)
+    and one with every turbine- and farm-level channel on (exercises the farm block: ghost farm-yaw slots that never
+    receive data, farm TI = calc_TI of the farm-mean ws ring -- SURVEY.md Q9-ii, Q10), one that runs into the
+    truncation (the reference counts ``timestep`` twice per step, WindEnvMulti.py:219 + Wind_Farm_Env.py:1027:
+    half-length episodes -- and raises in the truncating step, see make_multi)."""
+    return [
+        dict(name="multi_4x2_env1", cfg=small_config(4, 2, reward="Power_avg", action="yaw"), kw=dict(seed=5), steps=8),
+        dict(name="multi_rich_2x2", cfg=rich_config(2, 2, reward="Power_avg", action="wind"), kw=dict(seed=9), steps=12),
+        dict(name="multi_truncation", cfg=small_config(2, 1, reward="Power_avg", action="wind"),
+             kw=dict(seed=5, n_passthrough=0.2), steps=12),
+    ]
+
+
+def make_multi(ns, out):
+    """The UNMODIFIED ``WindFarmEnvMulti`` (WindEnvMulti.py:17-249).  Its constructor resets before
+    ``possible_agents`` exists; the pettingzoo shim's class attribute ``possible_agents = []`` lets that
+    first reset pass with no agents, the explicit ``reset(seed)`` below is the real one."""
+    Multi = ns.WindEnvMulti.WindFarmEnvMulti
+    meta = {}
+    for c in multi_cases():
+        path = write_yaml(c["cfg"])
+        env = Multi(V80(), yaml_path=path, turbtype="None", **c["kw"])
+        obs0, infos0 = env.reset(seed=c["kw"]["seed"])
+        agents = list(env.possible_agents)
+        T = env.n_turb
+        yaw0 = np.array(env.fs.windTurbines.yaw, dtype=np.float64).copy()
+        mt = dict(ws=float(env.ws), ti=float(env.ti), wd=float(env.wd), time_max=int(env.time_max),
+                  fs_time_after_reset=float(env.fs.time), declared_obs_var=int(env.obs_var), n_turb=T,
+                  obs_len=int(len(obs0[agents[0]])), cfg=c["cfg"], kw=c["kw"])
+        rng = np.random.default_rng(200 + c["kw"]["seed"])
+        acts = rng.uniform(-1, 1, (c["steps"], T)).astype(np.float32)
+        rec = {k: [] for k in ("obs", "reward", "trunc", "power", "yaw")}
+        for a in acts:
+            try:
+                o, r, te, tr, info = env.step({ag: a[i:i + 1] for i, ag in enumerate(agents)})
+            except AttributeError:
+                # The reference cannot return from the truncating step: WindFarmEnv.step tears the episode down
+                # (deletes farm_measurements, Wind_Farm_Env.py:1003-1023; SURVEY.md Q11) and WindFarmEnvMulti.step then
+                # reads them (WindEnvMulti.py:201).  What it pins is WHEN: the index of the truncating step, half the
+                # single-agent episode length because ``timestep`` is counted twice per step (Q9-iii).
+                mt["truncating_step"] = len(rec["obs"])
+                break
+            assert not any(te.values()) and len(set(r.values())) == 1 and len(set(tr.values())) == 1
+            rec["obs"].append(np.stack([o[ag] for ag in agents]))
+            rec["reward"].append(r[agents[0]])
+            rec["trunc"].append(tr[agents[0]])
+            if tr[agents[0]]:
+                assert env.agents == []          # the episode is over: infos is empty (no agents)
+                break
+            rec["power"].append(np.array([info[ag]["Power turbine agent"] for ag in agents]))
+            rec["yaw"].append(np.array([info[ag]["yaw angles agent"] for ag in agents]))
+        pre = c["name"]
+        n = len(rec["obs"])
+        out[f"{pre}/acts"], out[f"{pre}/yaw0"] = acts[:n], yaw0
+        out[f"{pre}/obs0"] = np.stack([obs0[ag] for ag in agents])
+        for k, v in rec.items():
+            out[f"{pre}/{k}"] = np.array(v)
+        mt["steps"] = n
+        meta[pre] = mt
+        os.unlink(path)
+    out["meta"] = np.array(json.dumps(meta))
+
+
+def make_cfg1(ns, out):
+    """BASELINE.json configs[0] exactly as stated: the shipped 2turb.yaml, seed 1, 200 steps on the CPU through the
+    reference's WindFarmEnv -- zero action for 100 steps, then +0.5."""
+    with open(os.path.join(ns.examples, "2turb.yaml")) as fh:
+        two = yaml.safe_load(fh)
+    path = write_yaml(two)
+    env = ns.WindFarmEnv(V80(), yaml_path=path, turbtype="None", seed=1)
+    obs0, _ = env.reset(seed=1)
+    T = env.n_turb
+    acts = np.zeros((200, T), dtype=np.float32)
+    acts[100:] = 0.5
+    rec = {k: [] for k in ("obs", "reward", "trunc", "power", "yaw", "power_base", "yaw_base", "ws_turb")}
+    out["cfg1/yaw0"] = np.array(env.fs.windTurbines.yaw, dtype=np.float64).copy()
+    for a in acts:
+        o, r, te, tr, info = env.step(a)
+        assert te is False and not tr
+        rec["obs"].append(o); rec["reward"].append(r); rec["trunc"].append(tr)
+        rec["power"].append(np.array(info["Power pr turbine agent"]))
+        rec["yaw"].append(np.array(info["yaw angles agent"]).copy())
+        rec["ws_turb"].append(np.array(info["Wind speed at turbines"]))
+        if env.Baseline_comp:
+            rec["power_base"].append(np.array(info["Power pr turbine baseline"]))
+            rec["yaw_base"].append(np.array(info["yaw angles base"]).copy())
+    out["cfg1/acts"], out["cfg1/obs0"] = acts, obs0
+    for k, v in rec.items():
+        out[f"cfg1/{k}"] = np.array(v)
+    out["meta"] = np.array(json.dumps({"cfg1": dict(
+        cfg=two, ws=float(env.ws), ti=float(env.ti), wd=float(env.wd), time_max=int(env.time_max),
+        obs_var=int(env.obs_var), n_turb=T, steps=200, fs_time_end=float(env.fs.time),
+        Baseline_comp=bool(env.Baseline_comp))}))
+    os.unlink(path)
+
+
 def main():
     ns = load_reference()
-    mes, env = {}, {}
-    make_mes(ns, mes)
-    np.savez_compressed(os.path.join(HERE, "mes_golden.npz"), **mes)
-    make_env(ns, env)
-    np.savez_compressed(os.path.join(HERE, "env_golden.npz"), **env)
-    for f in ("mes_golden.npz", "env_golden.npz"):
-        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+    only = sys.argv[1:]   # e.g. `make_golden.py multi cfg1` regenerates just those files
+    jobs = {"mes": (make_mes, "mes_golden.npz"), "env": (make_env, "env_golden.npz"),
+            "multi": (make_multi, "multi_golden.npz"), "cfg1": (make_cfg1, "cfg1_golden.npz")}
+    for key, (fn, fname) in jobs.items():
+        if only and key not in only:
+            continue
+        data = {}
+        fn(ns, data)
+        np.savez_compressed(os.path.join(HERE, fname), **data)
+        print(fname, os.path.getsize(os.path.join(HERE, fname)), "bytes")
 
 
 if __name__ == "__main__":

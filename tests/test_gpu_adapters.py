@@ -206,8 +206,11 @@ def test_step_host_equals_step(built_lib):
     pinned = torch.from_numpy(acts).pin_memory()
     for k in range(5):
         o, r, _, tr, _ = a.step(torch.as_tensor(acts[k]))
-        src = pinned[k] if k % 2 else acts[k]          # pinned tensor and pageable numpy array both work
+        # numpy array (staged into the env's pinned buffer), caller's pinned tensor (zero-copy as it is), pageable
+        # tensor (copy-engine fallback inside wg_step_host): all three give the device step's bits
+        src = (acts[k], pinned[k], torch.from_numpy(acts[k].copy()))[k % 3]
         oh, rh, th = b.step_host(src)
+        assert np.array_equal(b.obs.cpu().numpy(), oh)   # the device-side result buffer is written as well
         assert oh.dtype == np.float32 and rh.dtype == np.float32 and th.dtype == np.bool_
         assert np.array_equal(oh, o.cpu().numpy()) and np.array_equal(rh, r.cpu().numpy())
         assert np.array_equal(th, tr.cpu().numpy().astype(bool))

@@ -213,3 +213,63 @@ def test_farm_mes_env1_known_answer():                  # SURVEY.md 8(c) golden 
                    dtype=np.float32)
     assert np.array_equal(fm.get(True).astype(np.float32), exp)
     assert fm.n_out() == 8
+
+
+# ------------------------------------------------------------------------------------------------ multi-agent golden
+MULTI_CASES = ["multi_4x2_env1", "multi_rich_2x2", "multi_truncation"]
+
+
+@pytest.mark.parametrize("case", MULTI_CASES)
+def test_multi_agent_golden(case):
+    """Oracle's per-agent split (FarmMesO.get_multi) == the unmodified WindFarmEnvMulti._get_obs_multi
+    (WindEnvMulti.py:79-103), bit for bit; shared reward; the reference's half-length episodes."""
+    z, meta = _load("multi_golden.npz")
+    m = meta[case]
+    kw = dict(m["kw"])
+    seed = kw.pop("seed")
+    kw.setdefault("n_passthrough", 20)                       # WindFarmEnvMulti's default (WindEnvMulti.py:25)
+    env = WindFarmEnvOracle(V80(), m["cfg"], seed=seed, reset_init=True, **kw)
+    env.reset(seed=seed)
+    assert (env.ws, env.ti, env.wd, env.time_max) == (m["ws"], m["ti"], m["wd"], m["time_max"])
+    assert env.fs.time == m["fs_time_after_reset"]
+    assert np.array_equal(np.asarray(env.fs.windTurbines.yaw), z[f"{case}/yaw0"])
+    o0 = np.stack(env.mes.get_multi())
+    # declared obs dim over-counts by the farm-yaw ghost channels that never receive data (SURVEY.md Q9-ii)
+    assert o0.shape == (m["n_turb"], m["obs_len"]) and m["obs_len"] <= m["declared_obs_var"]
+    assert np.array_equal(o0, z[f"{case}/obs0"])
+    for k, a in enumerate(z[f"{case}/acts"]):
+        o, r, _, tr, info = env.step(a)
+        assert not tr
+        assert np.array_equal(np.stack(env.mes.get_multi()), z[f"{case}/obs"][k]), f"{case} step {k}"
+        assert r == pytest.approx(float(z[f"{case}/reward"][k]), rel=1e-12, abs=1e-12)
+        assert np.allclose(info["Power pr turbine agent"], z[f"{case}/power"][k], rtol=1e-12)
+        assert np.allclose(info["yaw angles agent"], z[f"{case}/yaw"][k], rtol=0, atol=1e-12)
+        env.timestep += 1                                    # the second increment of WindEnvMulti.py:219
+    if "truncating_step" in m:
+        # the next step is the one the reference truncates in (and cannot return from, see make_golden.make_multi)
+        assert len(z[f"{case}/acts"]) == m["truncating_step"]
+        assert env.timestep >= env.time_max and (env.timestep - 2) < env.time_max
+        assert m["truncating_step"] == (m["time_max"] + 1) // 2
+
+
+def test_cfg1_2turb_200_steps_golden():
+    """BASELINE.json configs[0]: shipped 2turb.yaml, seed 1, 200 CPU steps (zero action, then +0.5)."""
+    z, meta = _load("cfg1_golden.npz")
+    m = meta["cfg1"]
+    env = WindFarmEnvOracle(V80(), m["cfg"], seed=1, reset_init=True)
+    obs0, _ = env.reset(seed=1)
+    assert (env.ws, env.ti, env.wd, env.time_max, env.obs_var) == (m["ws"], m["ti"], m["wd"], m["time_max"], m["obs_var"])
+    assert np.array_equal(obs0, z["cfg1/obs0"])
+    acts = z["cfg1/acts"]
+    assert acts.shape == (200, 2) and np.all(acts[:100] == 0) and np.all(acts[100:] == 0.5)
+    for k, a in enumerate(acts):
+        o, r, term, tr, info = env.step(a)
+        assert term is False and not tr
+        assert np.array_equal(o, z["cfg1/obs"][k]), f"step {k}"
+        assert r == pytest.approx(float(z["cfg1/reward"][k]), rel=1e-12, abs=1e-12)
+        assert np.allclose(info["Power pr turbine agent"], z["cfg1/power"][k], rtol=1e-12)
+        assert np.allclose(info["Power pr turbine baseline"], z["cfg1/power_base"][k], rtol=1e-12)
+        assert np.allclose(info["yaw angles agent"], z["cfg1/yaw"][k], rtol=0, atol=1e-12)
+    assert env.fs.time == m["fs_time_end"]
+    # the yaw offsets moved by +0.5 * yaw_step per step in the second half ("yaw" action) or towards the set point
+    assert not np.allclose(z["cfg1/yaw"][99], z["cfg1/yaw"][199])

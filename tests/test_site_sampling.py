@@ -43,3 +43,33 @@ def test_site_sampling_is_clipped_and_seeded():
     assert a[2].min() >= 260 and a[2].max() <= 280 and a[0].min() >= 8 and a[0].max() <= 9
     assert (a[2] == 260).any() and (a[2] == 280).any()              # directions outside the range are clipped, not rejected
     assert len(np.unique(a[0])) > 10                                 # wind speeds vary (test_basics.py:369-407)
+
+
+def _shell(site, n_envs, yaw_mode="Zeros"):
+    env = VecWindFarmEnv.__new__(VecWindFarmEnv)
+    env.ec = types.SimpleNamespace(yaw_init_mode=yaw_mode, yaw_start=15.0, turbtype="None", ws_min=4, ws_max=20,
+                                   TI_min=0.02, TI_max=0.15, wd_min=200, wd_max=330)
+    env.n_envs, env.n_turb, env.sample_site, env._site_tables = n_envs, 2, site, None
+    env.ws, env.ti, env.wd = np.zeros(n_envs), np.zeros(n_envs), np.zeros(n_envs)
+    env._wind_override, env._episode, env.yaw_initial = {}, 1, [0]
+    return env
+
+
+def test_site_sampling_with_pinned_wind_and_defined_yaw_touches_every_env():
+    """Regression (round-1 advisor finding): the sector draw used to overwrite the env index list, so that
+    set_wind_vals applied to one env and yaw_init='Defined' indexed out of bounds."""
+    site = WeibullSite(np.full(12, 1 / 12), A=np.full(12, 9.0), k=np.full(12, 2.2))
+    env = _shell(site, 400, yaw_mode="Defined")
+    env.set_wind_vals(ws=11.5, wd=271.0)
+    env.set_yaw_vals([5.0, -7.0])
+    ws, ti, wd, yaw0 = env.sample_conditions(seed=5)
+    assert np.all(ws == 11.5) and np.all(wd == 271.0)               # the override reaches all 400 envs
+    assert len(np.unique(ti)) > 100                                  # TI still sampled per env
+    assert np.array_equal(yaw0, np.tile([5.0, -7.0], (400, 1)))
+    env4 = _shell(site, 4, yaw_mode="Defined")                       # B=4: used to raise IndexError (index 37)
+    env4.set_yaw_vals([3.0])
+    assert np.array_equal(env4.sample_conditions(seed=1)[3], np.full((4, 2), 3.0))
+    # masked subset: only the selected envs change
+    env.ws[:] = -1.0
+    ws2, *_ = env.sample_conditions(seed=5, envs=[3, 7])
+    assert np.all(ws2[[3, 7]] == 11.5) and np.all(np.delete(ws2, [3, 7]) == -1.0)

@@ -1,5 +1,6 @@
 // C-ABI of libwindgym_b200 (declared in include/windgym_b200.h): handle, state layout, launch orchestration.
 // Host-side only; the kernels live in flow.cu and env.cu.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -7,7 +8,15 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "wg_internal.cuh"
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define WG_CPU_RELAX() _mm_pause()
+#else
+#define WG_CPU_RELAX() ((void)0)
+#endif
 
 namespace {
 
@@ -54,6 +63,22 @@ struct wg_handle {
   int order_n = 0;                    // ... and its active count
   int order_age = 0;                  // wg_step calls since the last rebuild
   bool use_order = true;              // WG_NO_ORDER=1 in the environment: plain index order (A/B measurements)
+  // work table of single-step launches (wg_plan_kernel): resident CTA slots of the flow kernel variant in use
+  // (queried once per attached turbulence set-up), table capacity, tail-split policy
+  int slots = 0;
+  int work_cap = 0;
+  int n_work = 0;                     // entries of the current table
+  int tail_units = 0, tail_parts = 1; // WG_TAIL_UNITS / WG_TAIL_PARTS in the environment (A/B measurements)
+  bool use_split = true;              // WG_NO_SPLIT=1: never cut a farm into parts
+  // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
+  // number, and the pinned host ranges already identified (host base, device alias, bytes)
+  unsigned* flag_host = nullptr;
+  unsigned* flag_dev = nullptr;       // device alias of flag_host
+  unsigned* d_done_count = nullptr;
+  unsigned seq = 0;
+  bool use_zero_copy = true;          // WG_NO_ZEROCOPY=1: always stage through the copy engines
+  struct PinnedRange { const char* host; char* dev; size_t bytes; };
+  std::vector<PinnedRange> pinned;
   // L2 residency of the turbulence box: streams that already carry the access-policy window
   std::vector<cudaStream_t> policy_streams;
   size_t tb_lp_bytes = 0;
@@ -119,6 +144,10 @@ wg::Dev bind(const wg_handle* h, void* state) {
   d.n_step = at<int>(state, h, "n_step");
   d.load = at<int>(state, h, "load");
   d.order = at<int>(state, h, "order");
+  d.part_acc = at<int>(state, h, "part_acc");
+  d.part_keep = at<int>(state, h, "part_keep");
+  d.part_arrive = at<int>(state, h, "part_arrive");
+  d.work = at<int2>(state, h, "work");
   d.yaw = at<float>(state, h, "yaw");
   d.u = at<float>(state, h, "u");
   d.v = at<float>(state, h, "v");
@@ -380,6 +409,18 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   }
   h->n_copy = (int)cf.size();
   add_field(h, "order", 1, {B});  // a permutation of the active envs, not per-env state: outside the copy table
+  // scratch of split farms (all zeros between launches) and the work table: not per-env state either
+  add_field(h, "part_acc", 1, {B, F, 5, T});
+  add_field(h, "part_keep", 1, {B, F, T});
+  add_field(h, "part_arrive", 1, {B, F});
+  h->work_cap = std::max(B * F * 2, 2048);
+  add_field(h, "work", 1, {h->work_cap, 2});
+  const char* no_zc = getenv("WG_NO_ZEROCOPY");
+  h->use_zero_copy = !(no_zc && no_zc[0] == '1');
+  const char* no_split = getenv("WG_NO_SPLIT");
+  h->use_split = !(no_split && no_split[0] == '1');
+  if (const char* tu = getenv("WG_TAIL_UNITS")) h->tail_units = std::max(0, atoi(tu));
+  if (const char* tp = getenv("WG_TAIL_PARTS")) h->tail_parts = std::min(std::max(1, atoi(tp)), WG_MAX_PARTS);
   h->state_bytes = (h->state_bytes + 255) / 256 * 256;
   if ((e = upload(&h->d_copy, cf.data(), cf.size())) != cudaSuccess) {
     wg_destroy(h);
@@ -394,6 +435,8 @@ void wg_destroy(wg_handle* h) {
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   cudaFree(h->d_tab_ws); cudaFree(h->d_tab_p); cudaFree(h->d_tab_ct); cudaFree(h->d_x); cudaFree(h->d_y);
   cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc); cudaFree(h->d_copy);
+  cudaFree(h->d_done_count);
+  if (h->flag_host) cudaFreeHost(h->flag_host);
   delete h;
 }
 
@@ -486,17 +529,37 @@ int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, v
   return WG_OK;
 }
 
-int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
-            void* cuda_stream) {
-  if (!h || !state || !actions || !obs || !reward || !truncated) return fail(WG_ERR_INVALID, "wg_step: null argument");
+// host_out: optional mapped host copies of the results + completion flag (wg_step_host's zero-copy path)
+static int step_impl(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
+                     void* cuda_stream, const wg::FinishArgs* host_out) {
   cudaStream_t s = (cudaStream_t)cuda_stream;
   pin_turbulence_in_l2(h, s);
   wg::Dev d = bind(h, state);
   d.Bg = h->n_active;
-  // launch order: rebuilt after a reset / env copy / change of the active set, and every WG_ORDER_PERIOD steps (the
-  // live-station counts drift slowly); more CTAs than resident slots is the only case where the order matters
-  if (h->use_order && (h->order_state != state || h->order_n != d.Bg || ++h->order_age >= WG_ORDER_PERIOD)) {
-    WG_LAUNCH(wg::launch_order(d, s), "wg_order_kernel");
+  // launch order / work table: rebuilt after a reset / env copy / change of the active set, and every WG_ORDER_PERIOD
+  // steps (the live-station counts drift slowly).  Single-substep steps go by the work table (farms cut into parts
+  // when the batch leaves CTA slots free, or at the tail of the grid); others by the per-env order.
+  const bool by_table = h->use_split && d.S == 1;
+  if ((h->use_order || by_table) && (h->order_state != state || h->order_n != d.Bg || ++h->order_age >= WG_ORDER_PERIOD)) {
+    if (by_table) {
+      if (h->slots <= 0) h->slots = wg::flow_resident_ctas(d);
+      const int U = d.Bg * d.F;
+      wg::PlanArgs pa{};
+      pa.slots = h->slots;
+      if (U < h->slots) {
+        pa.n_work = h->slots;
+      } else {
+        pa.tail_units = std::min(h->tail_units, U);
+        pa.tail_parts = pa.tail_units > 0 ? h->tail_parts : 1;
+        pa.n_work = U + pa.tail_units * (pa.tail_parts - 1);
+      }
+      pa.n_work = std::min(pa.n_work, h->work_cap);
+      if (pa.n_work < U) return fail(WG_ERR_INVALID, "wg_step: work table too small");
+      h->n_work = pa.n_work;
+      WG_LAUNCH(wg::launch_plan(d, pa, s), "wg_plan_kernel");
+    } else {
+      WG_LAUNCH(wg::launch_order(d, s), "wg_order_kernel");
+    }
     h->order_state = state; h->order_n = d.Bg; h->order_age = 0;
   }
   cudaEvent_t* ev = nullptr;
@@ -515,15 +578,26 @@ int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* 
   }
   wg::FlowArgs fa{};
   fa.mode = wg::FLOW_STEP; fa.actions = actions; fa.farm_mask = (1 << d.F) - 1; fa.controller_on = 1;
-  fa.order = h->use_order ? d.order : nullptr;
+  if (by_table) { fa.work = d.work; fa.n_work = h->n_work; }
+  else fa.order = h->use_order ? d.order : nullptr;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
   if (ev) cudaEventRecord(ev[1], s);
   wg::FinishArgs fin{};
   fin.flags = wg::FIN_PUSH_MES | wg::FIN_PUSH_FP | (d.F > 1 ? wg::FIN_PUSH_BP : 0) | wg::FIN_OBS | wg::FIN_REWARD;
   fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
+  if (host_out) {
+    fin.obs_h = host_out->obs_h; fin.reward_h = host_out->reward_h; fin.truncated_h = host_out->truncated_h;
+    fin.done_count = host_out->done_count; fin.done_flag = host_out->done_flag; fin.seq = host_out->seq;
+  }
   WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(step)");
   if (ev) cudaEventRecord(ev[2], s);
   return WG_OK;
+}
+
+int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
+            void* cuda_stream) {
+  if (!h || !state || !actions || !obs || !reward || !truncated) return fail(WG_ERR_INVALID, "wg_step: null argument");
+  return step_impl(h, state, actions, obs, reward, truncated, cuda_stream, nullptr);
 }
 
 int wg_result_bytes(const wg_handle* h, size_t* out) {
@@ -531,6 +605,44 @@ int wg_result_bytes(const wg_handle* h, size_t* out) {
   const size_t B = (size_t)h->cfg.n_envs;
   *out = B * (size_t)h->dev.obs_rows * (size_t)h->dev.obs_dim * 4 + B * 4 + B;
   return WG_OK;
+}
+
+// Device alias of a host pointer if [p, p + bytes) lies in pinned (page-locked, mapped) host memory, else null.
+// Ranges found once are remembered per handle (a lookup costs a driver call otherwise).
+static char* pinned_alias(wg_handle* h, const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (const auto& r : h->pinned)
+    if (c >= r.host && c + bytes <= r.host + r.bytes) return r.dev + (c - r.host);
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost || !at.devicePointer) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  // the whole allocation, so that later sub-ranges (another row of the same pinned action buffer) hit the cache
+  CUdeviceptr base = 0;
+  size_t len = 0;
+  char* dev = reinterpret_cast<char*>(at.devicePointer);
+  // driver entry point resolved through the runtime: the library carries no link-time dependency on libcuda
+  typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static range_fn get_range = nullptr;
+  static bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      get_range = reinterpret_cast<range_fn>(fn);
+    cudaGetLastError();
+  }
+  if (get_range && get_range(&base, &len, (CUdeviceptr)at.devicePointer) == CUDA_SUCCESS && base && len) {
+    const size_t off = (size_t)((CUdeviceptr)at.devicePointer - base);
+    if (off + bytes > len) return nullptr;
+    if (h->pinned.size() < 64) h->pinned.push_back({c - off, dev - off, len});
+  } else if (h->pinned.size() < 64) {
+    h->pinned.push_back({c, dev, bytes});
+  }
+  return dev;
 }
 
 int wg_step_host(wg_handle* h, void* state, const float* actions_host, float* actions_dev, void* out_dev, void* out_host,
@@ -543,10 +655,58 @@ int wg_step_host(wg_handle* h, void* state, const float* actions_host, float* ac
   cudaStream_t s = (cudaStream_t)cuda_stream;
   const size_t B = (size_t)h->cfg.n_envs;
   const size_t act_bytes = (size_t)h->n_active * (size_t)h->cfg.n_turb * (size_t)h->dev.act_var * sizeof(float);
-  cudaError_t e = cudaMemcpyAsync(actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return cuda_fail(e, "wg_step_host: actions H2D");
   unsigned char* o = reinterpret_cast<unsigned char*>(out_dev);
   const size_t obs_bytes = B * (size_t)h->dev.obs_rows * (size_t)h->dev.obs_dim * 4;
+  cudaError_t e;
+
+  // Zero-copy path (both host buffers pinned): the flow kernel reads the actions straight from mapped host memory,
+  // the finish kernel stores obs | reward | truncated into the mapped result buffer and publishes the step number;
+  // the host polls that word.  No copy engine, no stream synchronisation in the step.
+  char* act_alias = h->use_zero_copy ? pinned_alias(h, actions_host, act_bytes) : nullptr;
+  char* out_alias = act_alias ? pinned_alias(h, out_host, out_bytes) : nullptr;
+  if (act_alias && out_alias) {
+    if (!h->flag_host) {
+      if ((e = cudaHostAlloc(reinterpret_cast<void**>(&h->flag_host), 64, cudaHostAllocMapped)) != cudaSuccess)
+        return cuda_fail(e, "wg_step_host: cudaHostAlloc");
+      h->flag_host[0] = 0;
+      if ((e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->flag_dev), h->flag_host, 0)) != cudaSuccess)
+        return cuda_fail(e, "wg_step_host: cudaHostGetDevicePointer");
+      if ((e = cudaMalloc(&h->d_done_count, sizeof(unsigned))) != cudaSuccess ||
+          (e = cudaMemset(h->d_done_count, 0, sizeof(unsigned))) != cudaSuccess)
+        return cuda_fail(e, "wg_step_host: completion counter");
+    }
+    wg::FinishArgs ho{};
+    ho.obs_h = reinterpret_cast<float*>(out_alias);
+    ho.reward_h = reinterpret_cast<float*>(out_alias + obs_bytes);
+    ho.truncated_h = reinterpret_cast<uint8_t*>(out_alias + obs_bytes + B * 4);
+    ho.done_count = h->d_done_count;
+    ho.done_flag = h->flag_dev;
+    ho.seq = ++h->seq;
+    if (ho.seq == 0) ho.seq = ++h->seq;  // 0 is the flag's rest value
+    const int rc = step_impl(h, state, reinterpret_cast<const float*>(act_alias), reinterpret_cast<float*>(o),
+                             reinterpret_cast<float*>(o + obs_bytes), o + obs_bytes + B * 4, cuda_stream, &ho);
+    if (rc != WG_OK) return rc;
+    volatile unsigned* flag = h->flag_host;
+    unsigned spins = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (*flag != ho.seq) {
+      WG_CPU_RELAX();
+      if ((++spins & 0x3fffu) == 0) {  // every ~16k polls: did the stream die, or is this taking absurdly long?
+        e = cudaStreamQuery(s);
+        if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "wg_step_host: stream failed");
+        if (e == cudaSuccess && *flag != ho.seq)
+          return fail(WG_ERR_CUDA, "wg_step_host: stream drained without publishing the step (lost completion flag)");
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30))
+          return fail(WG_ERR_CUDA, "wg_step_host: no completion after 30 s");
+      }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return WG_OK;
+  }
+
+  // pageable host memory: stage through the copy engines and synchronise the stream
+  if ((e = cudaMemcpyAsync(actions_dev, actions_host, act_bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+    return cuda_fail(e, "wg_step_host: actions H2D");
   const int rc = wg_step(h, state, actions_dev, reinterpret_cast<float*>(o), reinterpret_cast<float*>(o + obs_bytes),
                          o + obs_bytes + B * 4, cuda_stream);
   if (rc != WG_OK) return rc;
@@ -562,6 +722,7 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   wg::Dev& d = h->dev;
   if (!raw_uvw0 && !lp_vw) {  // back to uniform inflow
     d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr;
+    h->slots = 0; h->order_state = nullptr;
     return WG_OK;
   }
   if (!raw_uvw0 || !lp_vw) return fail(WG_ERR_INVALID, "wg_set_turbulence: both box layouts are required");
@@ -577,6 +738,7 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   d.tb_len_x = (float)((double)nx * (double)dx);
   h->tb_lp_bytes = (size_t)nx * ny * nz * sizeof(float2);
   h->policy_streams.clear();
+  h->slots = 0; h->order_state = nullptr;  // another kernel variant: resident-CTA count and work table are stale
   return WG_OK;
 }
 
@@ -586,6 +748,7 @@ int wg_set_added_turbulence(wg_handle* h, const float* iso_uvw0, int32_t nx, int
   wg::Dev& d = h->dev;
   if (!iso_uvw0) {
     d.tb2_raw = nullptr;
+    h->slots = 0; h->order_state = nullptr;
     return WG_OK;
   }
   if (!d.tb_raw) return fail(WG_ERR_INVALID, "wg_set_added_turbulence: attach the ambient box (wg_set_turbulence) first");
@@ -598,6 +761,7 @@ int wg_set_added_turbulence(wg_handle* h, const float* iso_uvw0, int32_t nx, int
   d.tb2_inv_n[0] = 1.f / nx; d.tb2_inv_n[1] = 1.f / ny; d.tb2_inv_n[2] = 1.f / nz;
   d.tb2_len_x = (float)((double)nx * (double)dx);
   d.k_m1 = k_m1; d.k_m2 = k_m2;
+  h->slots = 0; h->order_state = nullptr;
   return WG_OK;
 }
 

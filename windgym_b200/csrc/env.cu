@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
         val = fminf(fmaxf(val, -1.0f), 1.0f);
       }
       a.obs[(size_t)b * n_out + o] = val;
+      if (a.obs_h) a.obs_h[(size_t)b * n_out + o] = val;
     }
   }
 
@@ -259,8 +260,22 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     }
     a.reward[b] = (float)rew;
     const int ts = g_ts;
-    a.truncated[b] = ts >= g_tmax ? 1 : 0;  // Wind_Farm_Env.py:1003, :1027
+    const uint8_t tr = ts >= g_tmax ? 1 : 0;  // Wind_Farm_Env.py:1003, :1027
+    a.truncated[b] = tr;
+    if (a.reward_h) { a.reward_h[b] = (float)rew; a.truncated_h[b] = tr; }
     d.timestep[b] = ts + 1;
+  }
+  if (a.done_flag) {  // host-visible completion: every lane's host stores, then one arrival per env
+    __threadfence_system();
+    __syncwarp();
+    if (lane == 0) {
+      const unsigned t = atomicAdd(a.done_count, 1u);
+      if (t == (unsigned)d.Bg - 1u) {
+        *a.done_count = 0u;
+        __threadfence_system();
+        *a.done_flag = a.seq;
+      }
+    }
   }
 }
 
@@ -317,7 +332,11 @@ cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(float) * WG_FIN_WARPS * ((size_t)d.ring_floats + 2 * (size_t)d.power_avg);
   const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
   if (smem <= 100 * 1024) {
-    static size_t configured = 0;
+    static size_t configured_dev[WG_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= WG_MAX_DEVICES) dev = 0;
+    size_t& configured = configured_dev[dev];
     if (smem > 48 * 1024 && smem > configured) {
       cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e == cudaSuccess)
@@ -412,6 +431,110 @@ __global__ void __launch_bounds__(1024) wg_order_kernel(const int* __restrict__ 
 cudaError_t launch_order(const Dev& d, cudaStream_t s) {
   const int most = d.F * d.T * d.P;  // stations an env can hold
   wg_order_kernel<<<1, 1024, 0, s>>>(d.load, d.F, d.Bg, (most + WG_ORDER_BINS - 1) / WG_ORDER_BINS, d.order);
+  return cudaGetLastError();
+}
+
+// Work table of a single-step wg_step launch: which CTA streams which part of which farm (FlowArgs::work).
+//  * fewer farms than resident CTA slots (a GPU's share of a sharded batch, e.g. 512 envs): the farms are cut into
+//    parts of at most q tiles, q the smallest value whose part count fits the slots -- one wave that fills the
+//    machine, every CTA about equally long, instead of one CTA per farm with the launch as long as the heaviest farm;
+//  * more farms than slots: one CTA per farm, heaviest first; optionally the lightest `tail_units` farms, launched
+//    last, in `tail_parts` parts each, so that the grid drains on short CTAs.
+// Any split gives bit-identical results (fixed-point rotor sums, flow.cu).  One CTA; counting sort by tiles per part.
+#define WG_PLAN_BINS 1024
+__device__ __forceinline__ int plan_block_sum(int v, int* red) {  // all 1024 threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  int t = red[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+__device__ __forceinline__ void plan_exclusive_scan(int* hist, int* wsum) {  // hist[1024] in place, all 1024 threads
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int v = hist[tid];
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int w = wsum[lane];
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    wsum[lane] = winc - w;
+  }
+  __syncthreads();
+  hist[tid] = wsum[warp] + inc - v;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ load, int U, PlanArgs p,
+                                                       int2* __restrict__ work) {
+  __shared__ int hist[WG_PLAN_BINS];
+  __shared__ int wsum[32];
+  const int tid = threadIdx.x;
+  auto tiles = [&](int u) { return min(max((max(load[u], 0) + WG_TILE - 1) / WG_TILE, 1), WG_PLAN_BINS - 1); };
+  int q = WG_PLAN_BINS;  // tiles per part; >= every farm's tiles: no split
+  if (U < p.slots) {
+    int lo = 1, hi = WG_PLAN_BINS - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int n = 0;
+      for (int u = tid; u < U; u += blockDim.x) n += min((tiles(u) + mid - 1) / mid, WG_MAX_PARTS);
+      n = plan_block_sum(n, wsum);
+      if (n <= p.slots) hi = mid; else lo = mid + 1;
+    }
+    q = lo;
+  }
+  // rank of every farm by weight (bin 0 = heaviest): the tail rule needs it
+  hist[tid] = 0;
+  __syncthreads();
+  for (int u = tid; u < U; u += blockDim.x) atomicAdd(&hist[WG_PLAN_BINS - 1 - tiles(u)], 1);
+  __syncthreads();
+  plan_exclusive_scan(hist, wsum);
+  auto parts_of = [&](int u, int t) {
+    if (U < p.slots) return min((t + q - 1) / q, WG_MAX_PARTS);
+    const bool tail = p.tail_parts > 1 && hist[WG_PLAN_BINS - 1 - t] >= U - p.tail_units;
+    return tail ? min(p.tail_parts, WG_MAX_PARTS) : 1;
+  };
+  int np_mine[8], t_mine[8];  // up to 8192 farms per handle go through registers; more are recomputed
+  for (int k = 0, u = tid; u < U && k < 8; ++k, u += blockDim.x) { t_mine[k] = tiles(u); np_mine[k] = parts_of(u, t_mine[k]); }
+  __syncthreads();
+  hist[tid] = 0;
+  __syncthreads();
+  for (int k = 0, u = tid; u < U; ++k, u += blockDim.x) {
+    const int t = k < 8 ? t_mine[k] : tiles(u);
+    const int n = k < 8 ? np_mine[k] : 1;
+    atomicAdd(&hist[WG_PLAN_BINS - 1 - (t + n - 1) / n], n);
+  }
+  __syncthreads();
+  plan_exclusive_scan(hist, wsum);
+  for (int k = 0, u = tid; u < U; ++k, u += blockDim.x) {
+    const int t = k < 8 ? t_mine[k] : tiles(u);
+    const int n = k < 8 ? np_mine[k] : 1;
+    const int at = atomicAdd(&hist[WG_PLAN_BINS - 1 - (t + n - 1) / n], n);
+    for (int i = 0; i < n; ++i)
+      if (at + i < p.n_work) work[at + i] = make_int2(u, i | (n << 8));
+  }
+  __syncthreads();
+  // after the scatter the last bin's counter is the number of entries written
+  const int total = hist[WG_PLAN_BINS - 1];
+  for (int i = total + tid; i < p.n_work; i += blockDim.x) work[i] = make_int2(-1, 0);
+}
+
+cudaError_t launch_plan(const Dev& d, const PlanArgs& p, cudaStream_t s) {
+  wg_plan_kernel<<<1, 1024, 0, s>>>(d.load, d.Bg * d.F, p, d.work);
   return cudaGetLastError();
 }
 

@@ -32,6 +32,7 @@
 // fifth resident CTA per SM and let the march be a rolled loop that stays inside the instruction cache.
 #include <math_constants.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "wg_internal.cuh"
@@ -71,8 +72,12 @@ struct __align__(16) FlowShared {
   float tu[TURB ? TC : 1], tv[TURB ? TC : 1], tw[TURB ? TC : 1];  // rotor-averaged ambient fluctuation
   // TURB == 2 (wake-added turbulence): isotropic box sampled at every rotor's quadrature points, per-warp sums
   float iso[TURB == 2 ? 3 * TC * WG_NQ : 1];
-  float acc_ad[TURB == 2 ? 3 * WG_NWARP * TC : 1];
-  float acc_du[WG_NWARP][TC], acc_dv[WG_NWARP][TC];  // per-warp superposed deficit per rotor
+  // superposed deficit per rotor (and the wake-added turbulence, TURB == 2) as 32-bit fixed point, 2^-24 m/s per unit:
+  // integer addition is associative, so every warp (and every CTA of a split farm, see FlowArgs::work) adds its
+  // hits with shared / global atomics in ANY order and the sum is bit-identical -- alone, inside a batch, split or not
+  int acc_du[TC], acc_dv[TC];
+  int acc_ad[TURB == 2 ? 3 * TC : 1];
+  int ticket;                               // split farms: arrival ticket of this CTA (the last one runs the epilogue)
   int ord[TC];                              // turbine index of xs[k]
   int head[TC], count[TC], pre[TC + 1];
   // tile loop: index (from the oldest) of the chain's first station that stays in the farm after the NEXT step's
@@ -409,19 +414,36 @@ struct LaneLoc {
   int chain, slot, q, valid;
 };
 
-template <class SH>
+// Which chain / ring slot does flat station tile * 32 + lane belong to?  Farms of up to 32 chains: lane k reads the
+// inclusive prefix pre[k + 1]; two ballots give the chains of the tile's first and last station, the (rare) chain
+// boundaries inside the tile come by shuffle -- no dependent shared-memory search.  Larger farms: binary search.
+template <int TC, class SH>
 __device__ __forceinline__ LaneLoc locate(const SH& sh, int tile, int lane, int T, int P, int ntot) {
   LaneLoc L;
-  int fl = tile * WG_TILE + lane;
+  const int f0 = tile * WG_TILE;
+  int fl = f0 + lane;
   L.valid = fl < ntot;
   if (!L.valid) fl = ntot - 1;
-  int lo = 0, hi = T;
-  while (hi - lo > 1) {
-    int mid = (lo + hi) >> 1;
-    if (sh.pre[mid] <= fl) lo = mid; else hi = mid;
+  int lo;
+  if (TC <= 32) {
+    const unsigned full = 0xffffffffu;
+    const int pre_hi = lane < T ? sh.pre[lane + 1] : 0x7fffffff;
+    const int c0 = __popc(__ballot_sync(full, pre_hi <= f0));
+    const int c1 = __popc(__ballot_sync(full, pre_hi <= min(f0 + WG_TILE - 1, ntot - 1)));
+    lo = c0;
+    for (int c = c0; c < c1; ++c) lo += (fl >= __shfl_sync(full, pre_hi, c)) ? 1 : 0;
+    const int base = __shfl_sync(full, pre_hi, max(lo - 1, 0));
+    L.q = fl - (lo > 0 ? base : 0);
+  } else {
+    int hi = T;
+    lo = 0;
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (sh.pre[mid] <= fl) lo = mid; else hi = mid;
+    }
+    L.q = fl - sh.pre[lo];
   }
   L.chain = lo;
-  L.q = fl - sh.pre[lo];
   int s = sh.head[lo] - sh.count[lo] + L.q;
   L.slot = s < 0 ? s + P : s;
   return L;
@@ -445,39 +467,19 @@ __device__ __forceinline__ Seg segments(const LaneLoc& L, int lane) {
   return s;
 }
 
-// Per-rotor partial sums of one warp, spread over its lanes: lane l holds rotor l (and rotor l + 32 for farms
-// with more than 32 turbines).  Updates go through shuffles in hit order, so the result is bit-reproducible.
-template <int TC>
-struct RotorAcc {
-  float du0, dv0, du1, dv1;
-  float a0[3], a1[3];  // wake-added turbulence (u, v, w) of rotor l / l + 32 (TURB == 2 only)
-  __device__ __forceinline__ void clear() {
-    du0 = dv0 = du1 = dv1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) a0[k] = a1[k] = 0.f;
-  }
-  __device__ __forceinline__ void add_added(int lane, int j, float au, float av, float aw) {
-    if (lane == (j & 31)) {
-      if (TC <= 32 || j < 32) { a0[0] += au; a0[1] += av; a0[2] += aw; } else { a1[0] += au; a1[1] += av; a1[2] += aw; }
-    }
-  }
-  __device__ __forceinline__ void add(int lane, int j, float du, float dv) {
-    if (TC > 32) {
-      if (lane == (j & 31)) {
-        if (j < 32) { du0 += du; dv0 += dv; } else { du1 += du; dv1 += dv; }
-      }
-    } else if (lane == j) {
-      du0 += du; dv0 += dv;
-    }
-  }
-};
+// Fixed-point scale of the per-rotor sums: 2^24 units per m/s (resolution 6e-8 m/s, 16x finer than the float32 ulp of
+// a 10 m/s rotor speed; range +-128 m/s)
+#define WG_FX_SCALE 16777216.f
+#define WG_FX_INV (1.f / 16777216.f)
 
 // Evaluate the queued (station row, rotor) hits of one warp: two hits per pass, 16 quadrature points each on
-// 16 lanes, shuffle-reduced to the rotor average.
+// 16 lanes, shuffle-reduced to the rotor average; lanes 0 and 16 add the pass's two results to the farm's per-rotor
+// sums (shared-memory integer atomics: order-free, hence bit-reproducible however the tiles are distributed).
 template <int TC, int TURB>
 __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const uint32_t* __restrict__ hb, int nh,
-                                           RotorAcc<TC>& acc, int lane, float qy, float qz, const float* __restrict__ iso,
-                                           float k_m1, float k_m2) {
+                                           int* __restrict__ acc_du, int* __restrict__ acc_dv, int* __restrict__ acc_ad,
+                                           int lane, float qy, float qz, const float* __restrict__ iso, float k_m1,
+                                           float k_m2) {
   const unsigned full = 0xffffffffu;
   const int half = lane >> 4;
   for (int h0 = 0; h0 < nh; h0 += 2) {
@@ -494,8 +496,9 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
     float u1 = lds1(brow ^ ((uint32_t)(j0 + 1) << 2));
     if (j0 == WG_NR - 2) u1 = 1.f;
     float d = fmaf(fr, u0 - u1, 1.f - u0);  // (1-u0)(1-fr) + (1-u1) fr
-    const bool out = s >= (float)(WG_NR - 1) || !ok;
+    const bool out = s >= (float)(WG_NR - 1);
     if (out) d = 0.f;
+    const bool owner = ok && (lane & 15) == 0;  // a padded second hit adds nothing
     if (TURB == 2) {
       // wake-added turbulence: k_mt = k_m1 |1 - U| + k_m2 |dU/dr| at this point, times the station's weight w U0e
       // (|a.xy| with the sign of a.x: cos g0 > 0) and the isotropic box at (rotor bj, point lane & 15)
@@ -509,23 +512,21 @@ __device__ __forceinline__ void flush_hits(const float4* __restrict__ ha, const 
         av += __shfl_xor_sync(full, av, o);
         aw += __shfl_xor_sync(full, aw, o);
       }
-      const int jA = __shfl_sync(full, bj, 0), jB = __shfl_sync(full, bj, 16);
-      acc.add_added(lane, jA, __shfl_sync(full, au, 0) * (1.f / WG_NQ), __shfl_sync(full, av, 0) * (1.f / WG_NQ),
-                    __shfl_sync(full, aw, 0) * (1.f / WG_NQ));
-      acc.add_added(lane, jB, __shfl_sync(full, au, 16) * (1.f / WG_NQ), __shfl_sync(full, av, 16) * (1.f / WG_NQ),
-                    __shfl_sync(full, aw, 16) * (1.f / WG_NQ));
+      if (owner) {
+        atomicAdd(&acc_ad[bj], __float2int_rn(au * (WG_FX_SCALE / WG_NQ)));
+        atomicAdd(&acc_ad[TC + bj], __float2int_rn(av * (WG_FX_SCALE / WG_NQ)));
+        atomicAdd(&acc_ad[2 * TC + bj], __float2int_rn(aw * (WG_FX_SCALE / WG_NQ)));
+      }
     }
     d += __shfl_xor_sync(full, d, 8);
     d += __shfl_xor_sync(full, d, 4);
     d += __shfl_xor_sync(full, d, 2);
     d += __shfl_xor_sync(full, d, 1);
-    d *= (1.f / WG_NQ);
-    const float du = a.x * d, dv = a.y * d;
-    const float duA = __shfl_sync(full, du, 0), dvA = __shfl_sync(full, dv, 0);
-    const float duB = __shfl_sync(full, du, 16), dvB = __shfl_sync(full, dv, 16);
-    const int jA = __shfl_sync(full, bj, 0), jB = __shfl_sync(full, bj, 16);
-    acc.add(lane, jA, duA, dvA);
-    acc.add(lane, jB, duB, dvB);  // a padded second hit carries d = 0
+    if (owner) {
+      d *= (WG_FX_SCALE / WG_NQ);
+      atomicAdd(&acc_du[bj], __float2int_rn(a.x * d));
+      atomicAdd(&acc_dv[bj], __float2int_rn(a.y * d));
+    }
   }
 }
 
@@ -550,9 +551,19 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // wg_step launches the envs longest first (a.order): the CTAs that drain the grid are then the short ones
-  const int bi = F == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, f = F == 2 ? (int)(blockIdx.x & 1) : 0;  // F is 1 or 2
-  const int b = a.order ? a.order[bi] : bi;
-  const int bf = b * F + f;
+  // ... or, with a work table (wg_plan_kernel), one PART of a farm: CTA p of n streams the tiles 4 p + warp, + 4 n, ...
+  // of the farm's station list; the parts meet in global fixed-point sums and the last one to arrive runs the
+  // turbine epilogue (only for launches of a single flow step: nothing but the epilogue follows the tile loop)
+  int bf, part = 0, nparts = 1;
+  if (a.work) {
+    const int2 wk = __ldg(a.work + blockIdx.x);  // consumed after the TMEM allocation below (wk.x < 0: unused entry)
+    bf = wk.x; part = wk.y & 0xff; nparts = wk.y >> 8;
+  } else {
+    const int bi = F == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, f_blk = F == 2 ? (int)(blockIdx.x & 1) : 0;
+    if (!((a.farm_mask >> f_blk) & 1)) return;  // needs no load: before the TMEM allocation
+    bf = (a.order ? a.order[bi] : bi) * F + f_blk;
+  }
+  const int b = F == 2 ? bf >> 1 : bf, f = F == 2 ? bf & 1 : 0;  // F is 1 or 2
 #ifdef WG_TRACE
   const unsigned long long t_start = gtimer();
   unsigned long long t_p1 = 0, t_p2 = 0, t_p3 = 0, t_p4 = 0;
@@ -564,15 +575,32 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     atomicAdd(&g_phase[((blockIdx.x & 16383) * 4 + warp) * 8 + k], (unsigned long long)(now_ - ph_last));           \
     ph_last = now_;                                                         \
   }
+#define WG_TRACE_WRITE()                                                              \
+  if (tid == 0 && a.mode == FLOW_STEP && blockIdx.x < 65536) {                        \
+    unsigned smid;                                                                    \
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));                                 \
+    unsigned long long* tr = g_trace + 8 * blockIdx.x;                                \
+    tr[0] = t_start; tr[1] = gtimer(); tr[2] = smid | (nparts << 16) | (part << 24);  \
+    tr[3] = ((unsigned long long)b << 32) | (unsigned)sh.pre[T];                      \
+    tr[4] = t_p1; tr[5] = t_p2; tr[6] = t_p3; tr[7] = t_p4;                           \
+  }
 #else
 #define WG_STAMP(v)
 #define WG_PHASE(k)
+#define WG_TRACE_WRITE()
 #endif
-  if (!((a.farm_mask >> f) & 1)) return;
   // TMEM first: the SM starts the next CTA of a tcgen05-allocating kernel only after this one has given up its
   // allocation permit (measured, scripts/micro/cta_launch.cu: starts on an SM are spaced by the time to the
-  // relinquish -- 0.5 us when it is the first instruction, 2.9 us behind the prologue's loads)
+  // relinquish -- 0.5 us when it is the first instruction, 2.9 us behind the prologue's loads).  Nothing loaded from
+  // memory may be needed before this point (the work-table entry is first used below).
   if (warp == 0) tmem_alloc(&sh.tmem_base);
+  if (bf < 0) {  // unused entry of the work table (CTA-uniform): give the columns back
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (warp == 0) tmem_dealloc(sh.tmem_base);
+    return;
+  }
   // ---- prologue: every global load of the CTA is issued before the first use of any of them (one round trip to
   // L2 / HBM instead of a chain of them: each dependent group costs 0.6 - 0.8 us while the CTA holds its slot)
   const bool is_t = tid < T;
@@ -727,6 +755,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       const int c = sh.count[tid] - min(retire_r, sh.count[tid]);
       sh.count[tid] = c;
       sh.keep_emit[tid] = min(c, WG_RETIRE_CAP);
+      sh.acc_du[tid] = 0; sh.acc_dv[tid] = 0;
+      if (TURB == 2) { sh.acc_ad[tid] = 0; sh.acc_ad[TC + tid] = 0; sh.acc_ad[2 * TC + tid] = 0; }
     }
     if (TC > 32) __syncthreads(); else __syncwarp();
     if (warp == 0) {  // chain offsets in the flat station list: warp scan of the counts
@@ -749,13 +779,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     WG_STAMP(t_p2);
 
     // ------------------------------------------------------------------ warp-private tile pipeline
-    RotorAcc<TC> acc;
-    acc.clear();
     LaneLoc Ln;
     Ln.valid = 0; Ln.chain = 0; Ln.slot = 0; Ln.q = 0;
-    if (warp < ntiles) Ln = locate(sh, warp, lane, T, P, ntot);
+    const int tile0 = part * WG_NWARP + warp, tstride = nparts * WG_NWARP;
+    if (tile0 < ntiles) Ln = locate<TC>(sh, tile0, lane, T, P, ntot);
     WG_PHASE(0)  // outside the tile loop (prologue, step head, barriers, epilogue)
-    for (int tile = warp; tile < ntiles; tile += WG_NWARP) {
+    for (int tile = tile0; tile < ntiles; tile += tstride) {
       const LaneLoc Lc = Ln;
       const Seg sg = segments(Lc, lane);
       if (lane == 0) mbar_expect_tx(bar, (uint32_t)sg.nvalid * WG_ROW_BYTES);
@@ -785,8 +814,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
         pcx = __ldcg(reinterpret_cast<const float4*>(pcon + st_x * 4u));
       }
       // while the tile is in flight: find the next tile and pull its rows and scalars towards L2
-      if (tile + WG_NWARP < ntiles) {
-        Ln = locate(sh, tile + WG_NWARP, lane, T, P, ntot);
+      if (tile + tstride < ntiles) {
+        Ln = locate<TC>(sh, tile + tstride, lane, T, P, ntot);
         if (Ln.valid) {
           const unsigned st = (unsigned)(Ln.chain * P + Ln.slot);
           asm volatile("prefetch.global.L2 [%0];" ::"l"(prof + st * (unsigned)WG_NR));
@@ -913,7 +942,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
             }
             if (split) {
               __syncwarp();
-              flush_hits<TC, TURB>(ha, hb, nhA, acc, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
+              flush_hits<TC, TURB>(ha, hb, nhA, sh.acc_du, sh.acc_dv, sh.acc_ad, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
               __syncwarp();
             }
             if (hitB) {
@@ -923,7 +952,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
             }
             const int nh = split ? nhB : nhA + nhB;
             __syncwarp();
-            if (nh > 0) flush_hits<TC, TURB>(ha, hb, nh, acc, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
+            if (nh > 0) flush_hits<TC, TURB>(ha, hb, nh, sh.acc_du, sh.acc_dv, sh.acc_ad, lane, qy, qz, sh.iso, d.k_m1, d.k_m2);
             __syncwarp();
           }
         }
@@ -935,20 +964,48 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
       WG_PHASE(5)  // waiting for the store to release the buffer
     }
     WG_STAMP(t_p3);
-    if (lane < TC) {
-      sh.acc_du[warp][lane] = acc.du0;
-      sh.acc_dv[warp][lane] = acc.dv0;
-    }
-    if (TC > 32) {
-      sh.acc_du[warp][(lane + 32) % TC] = acc.du1;
-      sh.acc_dv[warp][(lane + 32) % TC] = acc.dv1;
-    }
-    if (TURB == 2) {
+    if (nparts > 1) {
+      // Split farm: add this CTA's sums to the farm's global ones and take an arrival ticket.  Every part but the last
+      // to arrive is done (its rows and station scalars are on their way to HBM); the last one collects the sums --
+      // leaving the scratch zeroed for the next step -- and runs the epilogue.  The retire prefix travels as
+      // WG_RETIRE_CAP - keep through atomicMax, so that the scratch's rest state is all zeros.
+      __syncthreads();
+      if (tid < T) {
+        int* ga = d.part_acc + (size_t)bf * (5 * T);
+        if (sh.acc_du[tid]) atomicAdd(ga + tid, sh.acc_du[tid]);
+        if (sh.acc_dv[tid]) atomicAdd(ga + T + tid, sh.acc_dv[tid]);
+        if (TURB == 2) {
 #pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        if (lane < TC) sh.acc_ad[(k * WG_NWARP + warp) * TC + lane] = acc.a0[k];
-        if (TC > 32) sh.acc_ad[(k * WG_NWARP + warp) * TC + (lane + 32) % TC] = acc.a1[k];
+          for (int k = 0; k < 3; ++k)
+            if (sh.acc_ad[k * TC + tid]) atomicAdd(ga + (2 + k) * T + tid, sh.acc_ad[k * TC + tid]);
+        }
+        const int kp = WG_RETIRE_CAP - sh.keep_emit[tid];
+        if (kp > 0) atomicMax(d.part_keep + (size_t)bf * T + tid, kp);
+        __threadfence();
       }
+      __syncthreads();
+      if (tid == 0) sh.ticket = atomicAdd(d.part_arrive + bf, 1);
+      __syncthreads();
+      if (sh.ticket != nparts - 1) {  // not the last part (CTA-uniform)
+        WG_TRACE_WRITE();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp == 0) tmem_dealloc(sh.tmem_base);
+        return;
+      }
+      __threadfence();
+      if (tid < T) {
+        int* ga = d.part_acc + (size_t)bf * (5 * T);
+        sh.acc_du[tid] = atomicExch(ga + tid, 0);
+        sh.acc_dv[tid] = atomicExch(ga + T + tid, 0);
+        if (TURB == 2) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) sh.acc_ad[k * TC + tid] = atomicExch(ga + (2 + k) * T + tid, 0);
+        }
+        sh.keep_emit[tid] = WG_RETIRE_CAP - atomicExch(d.part_keep + (size_t)bf * T + tid, 0);
+      }
+      if (tid == 0) d.part_arrive[bf] = 0;
     }
     if (TURB) {  // ambient fluctuation averaged over every rotor's quadrature points at the new time level
       for (int idx = tid; idx < T * WG_NQ; idx += blockDim.x) {  // T*16: half-warps stay whole
@@ -981,17 +1038,12 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     // ------------------------------------------------------------------ turbine epilogue
     const bool emit = (nstep % k_emit) == 0;
     if (tid < T) {
-      float du = 0.f, dv = 0.f;
-#pragma unroll
-      for (int wi = 0; wi < WG_NWARP; ++wi) { du += sh.acc_du[wi][tid]; dv += sh.acc_dv[wi][tid]; }
+      const float du = (float)sh.acc_du[tid] * WG_FX_INV, dv = (float)sh.acc_dv[tid] * WG_FX_INV;
       float u = ws - du + (TURB ? sh.tu[tid] : 0.f), v = dv + (TURB ? sh.tv[tid] : 0.f), w = TURB ? sh.tw[tid] : 0.f;
       if (TURB == 2) {
-#pragma unroll
-        for (int wi = 0; wi < WG_NWARP; ++wi) {
-          u += sh.acc_ad[(0 * WG_NWARP + wi) * TC + tid];
-          v += sh.acc_ad[(1 * WG_NWARP + wi) * TC + tid];
-          w += sh.acc_ad[(2 * WG_NWARP + wi) * TC + tid];
-        }
+        u += (float)sh.acc_ad[tid] * WG_FX_INV;
+        v += (float)sh.acc_ad[TC + tid] * WG_FX_INV;
+        w += (float)sh.acc_ad[2 * TC + tid] * WG_FX_INV;
       }
       const float yaw = sh.yaw[tid];
       float sg, cg;
@@ -1095,16 +1147,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
     }
   }
   if (tid == 0) {
-#ifdef WG_TRACE
-    if (a.mode == FLOW_STEP && blockIdx.x < 65536) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      unsigned long long* tr = g_trace + 8 * blockIdx.x;
-      tr[0] = t_start; tr[1] = gtimer(); tr[2] = smid;
-      tr[3] = ((unsigned long long)b << 32) | (unsigned)sh.pre[T];
-      tr[4] = t_p1; tr[5] = t_p2; tr[6] = t_p3; tr[7] = t_p4;
-    }
-#endif
+    WG_TRACE_WRITE();
     d.n_step[bf] = nstep;
     d.load[bf] = sh.pre[T];
     if (a.mode == FLOW_STEP && f == 1) d.base_pow_mean[b] = sh.base_sum / (float)nsteps;
@@ -1117,17 +1160,54 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
 }
 
 template <int TC, int TURB>
+constexpr size_t flow_smem() { return hdr_bytes<TC, TURB>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES; }
+
+template <int TC, int TURB>
 static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
-  const size_t smem = hdr_bytes<TC, TURB>() + (size_t)WG_NWARP * WG_TILE * WG_ROW_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  const size_t smem = flow_smem<TC, TURB>();
+  // the opt-in to > 48 KB of dynamic shared memory is a per-DEVICE function attribute: one flag per device, so that a
+  // process driving several GPUs configures each of them
+  static bool configured[WG_MAX_DEVICES] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= WG_MAX_DEVICES || !configured[dev]) {
     cudaError_t e =
         cudaFuncSetAttribute(wg_flow_kernel<TC, TURB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < WG_MAX_DEVICES) configured[dev] = true;
   }
-  wg_flow_kernel<TC, TURB><<<d.Bg * d.F, WG_NWARP * 32, smem, s>>>(d, a);
+  const int grid = a.work ? a.n_work : d.Bg * d.F;
+  wg_flow_kernel<TC, TURB><<<grid, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
+}
+
+// Resident CTAs per SM x SMs, from the kernel's own resource use.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor
+// answers 1 for this kernel -- it seems to charge a tcgen05-allocating kernel the whole tensor memory; measured
+// per-CTA timelines show 6 / 5 / 4 resident CTAs, i.e. registers and shared memory decide, as computed here.)
+template <int TC, int TURB>
+static int slots_as() {
+  int dev = 0, sms = 0, regs_sm = 0, smem_sm = 0, smem_rsv = 0;
+  cudaGetDevice(&dev);
+  cudaFuncAttributes fa{};
+  if (cudaFuncGetAttributes(&fa, wg_flow_kernel<TC, TURB>) != cudaSuccess) { cudaGetLastError(); return 0; }
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  cudaDeviceGetAttribute(&smem_rsv, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+  cudaGetLastError();
+  const int regs_warp = ((fa.numRegs + 7) / 8 * 8) * 32;                    // allocated per warp in units of 8 per thread
+  const int by_regs = regs_sm / (regs_warp * WG_NWARP);
+  const int by_smem = smem_sm / (int)(flow_smem<TC, TURB>() + fa.sharedSizeBytes + smem_rsv);
+  const int by_tmem = 512 / WG_TMEM_COLS;
+  const int per_sm = std::max(1, std::min(std::min(by_regs, by_smem), std::min(by_tmem, 32)));
+  return per_sm * sms;
+}
+
+// CTAs of the flow kernel variant this handle launches that are resident on the device at once
+int flow_resident_ctas(const Dev& d) {
+  if (d.tb_raw && d.tb2_raw) return d.T <= 16 ? slots_as<16, 2>() : slots_as<WG_MAX_T, 2>();
+  if (d.tb_raw) return d.T <= 16 ? slots_as<16, 1>() : slots_as<WG_MAX_T, 1>();
+  return d.T <= 16 ? slots_as<16, 0>() : slots_as<WG_MAX_T, 0>();
 }
 
 #ifdef WG_TRACE

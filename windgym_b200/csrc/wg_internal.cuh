@@ -11,6 +11,8 @@
 #define WG_MAX_T 64       // turbines per farm supported by the fixed-size shared tables
 #define WG_TILE 32        // stations per warp tile
 #define WG_ROW_BYTES (WG_NR * 4)
+#define WG_MAX_DEVICES 64  // per-device one-time kernel attribute set-up
+#define WG_MAX_PARTS 8     // CTAs one farm's station list can be split over (wg_plan_kernel)
 
 namespace wg {
 
@@ -76,6 +78,11 @@ struct Dev {
   int* n_step;            // [B,F]
   int* load;              // [B,F] live stations of the farm after its last flow step (work estimate of its CTA)
   int* order;             // [B]   launch order of wg_step: envs [0, Bg) sorted by descending load (see wg_order_kernel)
+  // split farms (FlowArgs::work): scratch the parts of a farm meet in; all zeros between launches
+  int* part_acc;          // [B,F,5,T] fixed-point rotor sums du, dv (+ wake-added u, v, w)
+  int* part_keep;         // [B,F,T]   WG_RETIRE_CAP - (retire prefix of the chain)
+  int* part_arrive;       // [B,F]     arrival counter
+  int2* work;             // [n_work]  work table of wg_step: (farm b*F+f | -1, part | nparts << 8), longest part first
   float *yaw, *u, *v, *w, *power, *ct;  // [B,F,T]
   float *derate;          // [B,F,T] induction scale delta in [derate_min, 1] (1 = the reference's turbine)
   // env state
@@ -112,6 +119,16 @@ struct FlowArgs {
   int farm_mask;        // bit f set: farm f advances
   int controller_on;    // baseline farm applies its greedy controller each substep
   const int* order;     // optional permutation of [0, Bg): CTA group i works on env order[i] (longest first)
+  const int2* work;     // optional work table (single-step launches only): CTA i works on part work[i]; replaces order
+  int n_work;           // entries of the table = CTAs of the launch
+};
+
+// how wg_plan_kernel cuts the farms of a step into CTAs
+struct PlanArgs {
+  int n_work;      // table entries (= CTAs launched); unused ones are marked -1
+  int slots;       // resident CTAs of the flow kernel on this device
+  int tail_units;  // more farms than slots: the lightest tail_units farms (launched last) are cut into
+  int tail_parts;  //   tail_parts parts each, so that the grid drains on short CTAs (1: no tail split)
 };
 
 struct FinishArgs {
@@ -119,6 +136,12 @@ struct FinishArgs {
   const uint8_t* mask;
   const float* in_ws; const float* in_wd; const float* in_yaw; const float* in_power;  // FIN_MEAS_FROM_ARGS
   float* obs; float* reward; uint8_t* truncated;
+  // wg_step_host with pinned host buffers: the results are ALSO stored straight into mapped host memory (no copy
+  // engine in the step) and the last warp to finish publishes the step's sequence number for the polling host
+  float* obs_h; float* reward_h; uint8_t* truncated_h;
+  unsigned* done_count;          // device counter of finished warps (back to 0 when the flag is written)
+  volatile unsigned* done_flag;  // mapped host word
+  unsigned seq;
 };
 
 struct ResetDevArgs {
@@ -217,6 +240,8 @@ void set_rotor_points(const float* qy, const float* qz);
 cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
 cudaError_t launch_order(const Dev& d, cudaStream_t s);
+cudaError_t launch_plan(const Dev& d, const PlanArgs& p, cudaStream_t s);
+int flow_resident_ctas(const Dev& d);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
 // one state field as the env-copy kernel sees it: n_rep blocks of B envs, per_env bytes each
 struct CopyField {

@@ -347,7 +347,9 @@ class WindFarmEnv(_GymEnv):
     def reset(self, seed=None, options=None):
         """Wind_Farm_Env.py:680-802.  Returns (obs float32[obs_var], info)."""
         if seed is not None:
-            self.vec._episode = 0  # gymnasium re-seeds np_random: same seed -> same episode (check_env determinism)
+            # gymnasium re-seeds np_random: same seed -> same episode (check_env determinism); later unseeded resets
+            # continue that stream (VecWindFarmEnv.reset stores the seed and rewinds its episode counter)
+            self.seed = seed
         obs, _ = self.vec.reset(seed=seed if seed is not None else self._next_seed())
         self.vec.check_flags()
         self.timestep = 0
@@ -432,7 +434,6 @@ class FarmEval(WindFarmEnv):
                 setattr(self, k, val)
 
     def set_yaw_vals(self, yaw_vals):
-        self.vec.ec.yaw_init_mode = "Defined" if self.vec.ec.yaw_init_mode == "Defined" else self.vec.ec.yaw_init_mode
         self.vec.set_yaw_vals(yaw_vals)
 
     def update_tf(self, path):

@@ -82,6 +82,11 @@ def eval_batched(env, model, windspeeds=(10.0,), winddirs=(270,), turbintensitie
     conds = condition_grid(windspeeds, winddirs, turbintensities, turbboxes)
     if any(b != "Default" for _, _, _, b in conds) and getattr(env.ec, "turbtype", "None") == "None":
         raise NotImplementedError("named turbulence boxes need a Mann-box site (turbtype != 'None')")
+    if len(set(turbboxes)) > 1:
+        # every env of a handle samples the handle's ONE shared box: a turbbox axis with several names would hold
+        # identical results (the reference loads a box per entry, AgentEval.py:110-118) -- refuse instead
+        raise NotImplementedError("eval_batched evaluates one turbulence box per call: run it once per box "
+                                  "(env.update_tf / turb_box=) and concatenate along 'turbbox'")
     use_dist = dist.is_initialized() and dist.get_world_size() > 1 if distributed is None else bool(distributed)
     rank, world = (dist.get_rank(), dist.get_world_size()) if use_dist else (0, 1)
     lo, hi = shard_range(len(conds), rank, world)

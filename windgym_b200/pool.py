@@ -120,6 +120,9 @@ class PooledVecEnv:
             if yaw0 is not None:
                 yaw0 = np.concatenate([np.broadcast_to(np.asarray(yaw0, dtype=np.float64), (B, self.n_turb)),
                                        np.zeros((R, self.n_turb))])
+            if seed is not None:   # spares prepared later continue the seeded stream
+                self.inner.seed = seed
+                self.inner._episode = 0
             self.inner.reset(seed=seed, mask=m, wind=wind, yaw0=yaw0)
             self._refill(list(range(B, B + R)))
             return self.obs, self._info()

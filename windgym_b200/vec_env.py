@@ -162,6 +162,7 @@ class VecWindFarmEnv:
                     f for ext in ("*.npz", "*.npy", "*.nc") for f in glob.glob(os.path.join(str(TurbBox), ext)))
                 if not files:
                     raise FileNotFoundError(f"TurbBox={TurbBox!r}: no turbulence box file (.npz/.npy/.nc) found")
+                self._tf_files = files
                 pick = np.random.default_rng(self.seed).choice(len(files))
                 box = MannBox.from_file(files[pick], device=self.device, lowpass_width=2 * ec.D)
         if box.device != self.device:
@@ -226,7 +227,7 @@ class VecWindFarmEnv:
         # against numpy in tests/test_host_logic.py) instead of one Generator object per env (17 us each).
         idx = np.fromiter(envs, dtype=np.int64)
         if (seed is not None and not (B == 1 and self._episode == 0) and self.sample_site is None
-                and ec.turbtype != "MannGenerate" and 0 <= int(seed) < 2 ** 32 and idx.size > 8
+                and ec.turbtype not in ("MannGenerate", "MannLoad") and 0 <= int(seed) < 2 ** 32 and idx.size > 8
                 and not getattr(self, "_no_fast_rng", False)):
             n_yaw = T if ec.yaw_init_mode == "Random" else 0
             u = uniform_streams(int(seed), idx, self._episode, 3 + n_yaw)
@@ -249,13 +250,15 @@ class VecWindFarmEnv:
                 wd[i] = rng.uniform(low=ec.wd_min, high=ec.wd_max)
             else:  # site-based sampling, Wind_Farm_Env.py:569-596 (sector frequency -> Weibull A, k -> clip)
                 dirs, As, ks, freqs = self._site()
-                idx = rng.choice(np.arange(dirs.size), 1, p=freqs)
-                wd_s, ws_s = dirs[idx].item(), (As[idx] * rng.weibull(ks[idx])).item()
+                sec = rng.choice(np.arange(dirs.size), 1, p=freqs)   # sector index (NOT the env index list `idx`)
+                wd_s, ws_s = dirs[sec].item(), (As[sec] * rng.weibull(ks[sec])).item()
                 wd[i] = np.clip(wd_s, ec.wd_min, ec.wd_max)
                 ws[i] = np.clip(ws_s, ec.ws_min, ec.ws_max)
                 ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
             if ec.turbtype == "MannGenerate":    # TF_seed draw sits between wd and yaw (Wind_Farm_Env.py:623)
                 self._tf_seed[i] = int(rng.integers(0, 100000))
+            elif ec.turbtype == "MannLoad":      # np_random.choice(TF_files) sits there too (:614): keep the stream aligned
+                rng.choice(max(1, len(getattr(self, "_tf_files", ()))))
             if ec.yaw_init_mode == "Random":
                 yaw0[i] = rng.uniform(low=-ec.yaw_start, high=ec.yaw_start, size=T)
         for k, arr in (("ws", ws), ("ti", ti), ("wd", wd)):
@@ -289,6 +292,11 @@ class VecWindFarmEnv:
         sel = np.arange(B) if mask is None else np.flatnonzero(np.asarray(mask))
         if seed is None:
             seed = self.seed
+        elif mask is None:
+            # an explicit seed restarts the stream: later unseeded (and masked auto-) resets continue it, and
+            # reset(seed=s) twice gives the same conditions (gymnasium check_env determinism)
+            self.seed = seed
+            self._episode = 0
         ws, ti, wd, y0 = self.sample_conditions(seed, sel)
         if wind is not None:
             for arr, v in zip((ws, ti, wd), wind):
@@ -353,11 +361,11 @@ class VecWindFarmEnv:
 
     def step_host(self, actions):
         """``step()`` for callers whose buffers live on the HOST (the reference's contract: numpy in, numpy out):
-        actions float32 [B, T*act_var] (numpy array or CPU tensor; pinned memory avoids a staging copy) are copied
-        to the device, the step runs, and obs / reward / truncated come back with ONE device-to-host copy into
-        pinned host memory.  Returns numpy views (obs [B,obs], reward [B], truncated bool [B]) that stay valid
-        until the next ``step_host`` call, after synchronising the stream; ``info`` stays on the device
-        (``self._info()``)."""
+        actions float32 [B, T*act_var] (numpy array or CPU tensor) in, numpy views out (obs [B,obs], reward [B],
+        truncated bool [B]; valid until the next ``step_host`` call), returned when the results are in host memory.
+        With pinned host buffers (``pin_memory()`` tensors; the result buffer always is) nothing is copied: the flow
+        kernel reads the actions from mapped host memory, the finish kernel writes the results there and the host
+        polls the step's completion word (``wg_step_host``).  ``info`` stays on the device (``self._info()``)."""
         if self._host is None:
             n_obs = int(np.prod(self.obs_shape))
             res = torch.empty(self._out.numel(), dtype=torch.uint8).pin_memory()
@@ -374,20 +382,25 @@ class VecWindFarmEnv:
             self._host.update(act_ptr=_ptr(self._host["act_dev"]), out_ptr=_ptr(self._out),
                               res_ptr=C.c_void_p(res.data_ptr()), n_res=C.c_size_t(nb.value))
         h = self._host
-        n_act = getattr(self, "n_active", self.n_envs)
-        a = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
-        if a.numel() != n_act * self.n_turb * self.ec.act_var:
-            raise ValueError(f"actions must have {n_act}x{self.n_turb * self.ec.act_var} elements")
-        a = a.to(torch.float32).contiguous().reshape(n_act, -1)
-        if not a.is_pinned():           # pageable source: stage through the pinned buffer (one host memcpy)
-            h["act"][:n_act].copy_(a)
-            a = h["act"][:n_act]
-        # one C-ABI call: H2D of the actions, the two kernels, D2H of the packed results, stream synchronise
-        rc = self.lib.wg_step_host(self._h, self._step_ptrs[0], C.c_void_p(a.data_ptr()), h["act_ptr"], h["out_ptr"],
+        n_need = getattr(self, "n_active", self.n_envs) * self.n_turb * self.ec.act_var
+        if (torch.is_tensor(actions) and actions.dtype == torch.float32 and actions.device.type == "cpu"
+                and actions.is_contiguous() and actions.numel() == n_need):
+            a_ptr = actions.data_ptr()       # fast path: the caller's buffer goes to the C-ABI as it is
+        else:
+            a = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.float32))
+            if a.numel() != n_need:
+                raise ValueError(f"actions must have {n_need // (self.n_turb * self.ec.act_var)}x"
+                                 f"{self.n_turb * self.ec.act_var} elements")
+            stage = h["act"].view(-1)[:n_need]
+            stage.copy_(a.reshape(-1))       # dtype / layout conversion into the pinned staging buffer
+            a_ptr = stage.data_ptr()
+        # one C-ABI call.  Pinned host buffers (the staging buffers here are; a caller's own pinned tensor too): the
+        # kernels read the actions from and write the results to mapped host memory directly and the call returns when
+        # the step's completion word arrives.  Pageable buffers: H2D copy, step, D2H copy, stream synchronise.
+        rc = self.lib.wg_step_host(self._h, self._step_ptrs[0], a_ptr, h["act_ptr"], h["out_ptr"],
                                    h["res_ptr"], h["n_res"], self._stream())
         if rc != 0:
             _lib.check(rc)
-        self._last_actions = h["act_dev"][:n_act]
         return h["obs"], h["reward"], h["truncated"]
 
     def set_active(self, n_active):
