@@ -163,6 +163,34 @@ int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float*
 int wg_set_active(wg_handle* h, int32_t n_active);
 int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* dst, int32_t n, void* cuda_stream);
 
+/* Device-side auto-reset: the host is not in the loop.  wg_pool_init makes the slots [n_active, n_envs) a pool of
+ * spare envs (wg_step advances the first n_active, like wg_set_active).  Per step, on the stepping stream:
+ * wg_pool_swap pairs the envs whose episode just ended (truncated[b] != 0, as written by wg_step) with READY spares
+ * and copies the spares' complete state over them -- swapped[b] = 1 marks the envs that start a new episode in this
+ * step (their obs row becomes the spare's reset observation, the finished episode's last observation is kept in
+ * final_obs when given); an episode that finds no ready spare runs on and is swapped in a later step.  Every few
+ * steps, on a background stream: wg_pool_refill takes the spares consumed so far, draws their wind conditions on
+ * the device (counter-based generator keyed by seed, slot and refill count; the reference draws ws, ti, wd, yaw in
+ * that order from np_random, Wind_Farm_Env.py:557-568,:715), runs WindFarmEnv.reset's spin-up + measurement fill on
+ * them (:722-766) and marks them READY.  mask_row in [0, 8): one per refill in flight (a row may be reused once the
+ * stream that carried its previous refill has drained it, e.g. row = stream index).  wg_pool_stats (synchronises):
+ * out[0] swaps, out[1] finished episodes deferred for lack of a ready spare (summed over steps), out[2] refills. */
+typedef struct {
+  double ws_min, ws_max, ti_min, ti_max, wd_min, wd_max; /* wind: ws_min ... (YAML "wind" section)              */
+  double yaw_start;        /* yaw_init "Random": uniform(-yaw_start, yaw_start) (:715)                          */
+  double n_passthrough;    /* time_max = int(t_inflow * n_passthrough) (:732)                                   */
+  double tb_std_u;         /* std(u) of the attached turbulence box (scale_TI, :617); ignored without a box     */
+  float yaw_const;         /* initial yaw offset when not random ("Zeros": 0)                                   */
+  int32_t yaw_random;
+  int32_t eval_mode;       /* FarmEval: time_max = 9999999                                                      */
+  uint64_t seed;
+} wg_pool_draw;
+int wg_pool_init(wg_handle* h, void* state, int32_t n_active, void* cuda_stream);
+int wg_pool_refill(wg_handle* h, void* state, const wg_pool_draw* draw, float* obs, int32_t mask_row, void* cuda_stream);
+int wg_pool_swap(wg_handle* h, void* state, const uint8_t* truncated, float* obs, uint8_t* swapped, float* final_obs,
+                 void* cuda_stream);
+int wg_pool_stats(wg_handle* h, void* state, uint64_t out[8], void* cuda_stream);
+
 /* TurbulenceFieldSite over a MannTurbulenceField (_def_site, Wind_Farm_Env.py:598-678): attach one periodic
  * turbulence box, shared read-only by every env of the handle, in the two layouts the flow kernel samples:
  * raw_uvw0 device [nx,ny,nz,4] f32 (u, v, w, 0) and lp_vw device [nx,ny,nz,2] f32 ((v, w) low-pass filtered in

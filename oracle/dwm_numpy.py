@@ -300,7 +300,15 @@ class DWMFlowSimulation:
     """Restated ``dynamiks.dwm.DWMFlowSimulation`` (reference ctor call ``Wind_Farm_Env.py:702-711``)."""
 
     def __init__(self, site, windTurbines, wind_direction=270.0, particleDeficitGenerator=None, dt=1,
-                 d_particle=0.2, particleMotionModel=None, addedTurbulenceModel=None, p_cap=None, **_):
+                 d_particle=0.2, particleMotionModel=None, addedTurbulenceModel=None, p_cap=None, emit_rule="cadence",
+                 **_):
+        # emit_rule (sensitivity studies only, tests/test_dwm_oracle_physics.py; the frozen specification -- and the
+        # CUDA kernel -- is "cadence"):
+        #   "cadence"  one particle per chain every k_emit = ceil(d_particle D / (ws dt)) steps
+        #   "distance" per chain, at the first step boundary where its newest particle has travelled >= d_particle D
+        #   int k      one particle per chain every k steps
+        self.emit_rule = emit_rule
+        self.d_emit = float(d_particle) * float(windTurbines.diameter())
         wt = windTurbines
         self.site, self.windTurbines = site, wt
         wt._fs = self
@@ -319,6 +327,8 @@ class DWMFlowSimulation:
         self.positions_xyz = np.stack([xr, yr, np.full(T, self.zh)])
         self.xmax = xr.max()
         self.k_emit = emission_cadence(d_particle, self.D, self.ws, self.dt)
+        if isinstance(emit_rule, (int, np.integer)) and not isinstance(emit_rule, bool):
+            self.k_emit = max(1, int(emit_rule))
         tab_ct = getattr(wt.windTurbine, "ct_table", np.array([0.9]))
         a_max = 0.5 * (1.0 - np.sqrt(1.0 - min(float(np.max(tab_ct)), CT_MAX)))
         self.f_min = 1.0 - K_HILL * 2.0 * a_max
@@ -433,13 +443,20 @@ class DWMFlowSimulation:
                 amb = amb + (kmt[None] * self.added.sample(px, py, pz, self.time + dt, self.ws)).mean(axis=2)
         self.rotor_avg_windspeed = np.stack([self.ws + amb[0] - du, amb[1] + dv, amb[2]], axis=1)
         # 4./5. turbine update and particle release
-        if self.n_step % self.k_emit == 0:
+        if self.emit_rule == "distance":
+            newest = (self.head - 1) % P
+            due = (self.count == 0) | (self.pmut[np.arange(T), newest, 0] - self.xr >= self.d_emit)
+        else:
+            due = np.full(T, self.n_step % self.k_emit == 0)
+        if due.any():
             u = self.rotor_avg_windspeed[:, 0]
             ct = np.clip(wt.ct(), 0.0, CT_MAX)
             a = 0.5 * (1.0 - np.sqrt(1.0 - ct))
             Uin = inlet_profile(a)
             g = np.deg2rad(wt.yaw)
             for t in range(T):
+                if not due[t]:
+                    continue
                 s = self.head[t]
                 if self.count[t] == P:
                     self.overflow += 1

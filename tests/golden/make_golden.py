@@ -16,6 +16,7 @@ Files (all small):
   multi_golden.npz WindFarmEnvMulti (WindEnvMulti.py) reset + step: per-agent observation split, shared reward,
                    half-length truncation
   cfg1_golden.npz  BASELINE.json configs[0]: shipped 2turb.yaml, seed 1, 200 steps (zero action, then +0.5)
+  ppo_golden.npz   the shipped agent examples/PPO_2975000.zip: actor weights + deterministic actions on fixed observations
 """
 import json
 import os
@@ -276,11 +277,39 @@ def make_cfg1(ns, out):
     os.unlink(path)
 
 
+def make_ppo(ns, out):
+    """The shipped agent ``/root/reference/examples/PPO_2975000.zip`` (SB3 2.3.2 MlpPolicy, 8 -> 64 -> 64 -> 4, tanh):
+    its actor weights and its deterministic actions on fixed observations, evaluated HERE with plain numpy from the raw
+    state dict (mean = action_net(tanh(W2 tanh(W1 o + b1) + b2)); predict(deterministic=True) = clip(mean, -1, 1)) --
+    independent of windgym_b200.agents.SB3MlpPolicy, which the tests compare against it."""
+    import io
+    import zipfile
+
+    import torch
+    path = os.path.join(os.path.dirname(ns.examples), "PPO_2975000.zip")
+    with zipfile.ZipFile(path) as z:
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+    w = {k: v.double().numpy() for k, v in sd.items()}
+    rng = np.random.default_rng(2975000)
+    obs = np.concatenate([rng.uniform(-1, 1, (64, 8)), np.zeros((1, 8)), np.ones((1, 8)), -np.ones((1, 8))]).astype(np.float32)
+    h = obs.astype(np.float64)
+    for i in (0, 2):
+        h = np.tanh(h @ w[f"mlp_extractor.policy_net.{i}.weight"].T + w[f"mlp_extractor.policy_net.{i}.bias"])
+    mean = h @ w["action_net.weight"].T + w["action_net.bias"]
+    out["obs"], out["actions"] = obs, np.clip(mean, -1.0, 1.0)
+    for k in sd:
+        if k.startswith("mlp_extractor.policy_net.") or k.startswith("action_net.") or k == "log_std":
+            out["sd/" + k] = sd[k].numpy()
+    out["meta"] = np.array(json.dumps({"source": "examples/PPO_2975000.zip", "obs_dim": 8, "n_actions": 4,
+                                       "hidden": [64, 64], "keys": sorted(sd.keys())}))
+
+
 def main():
     ns = load_reference()
     only = sys.argv[1:]   # e.g. `make_golden.py multi cfg1` regenerates just those files
     jobs = {"mes": (make_mes, "mes_golden.npz"), "env": (make_env, "env_golden.npz"),
-            "multi": (make_multi, "multi_golden.npz"), "cfg1": (make_cfg1, "cfg1_golden.npz")}
+            "multi": (make_multi, "multi_golden.npz"), "cfg1": (make_cfg1, "cfg1_golden.npz"),
+            "ppo": (make_ppo, "ppo_golden.npz")}
     for key, (fn, fname) in jobs.items():
         if only and key not in only:
             continue

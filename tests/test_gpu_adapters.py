@@ -15,7 +15,8 @@ def test_vector_env_autoreset_matches_fresh_reset(built_lib):
     cfg = small_config(2, 1, reward="Power_avg", action="yaw")
     B, T = 4, 2
     # n_passthrough tiny -> time_max = int(dist/ws * n_pass) is a handful of steps, different per env
-    env = RecordEpisodeVals(GymVectorEnv(V80(), B, config=cfg, n_passthrough=0.2, seed=5, device="cuda:0"))
+    # pooled=False: the masked in-step reset (exact reference RNG stream); the default is the device-side pool
+    env = RecordEpisodeVals(GymVectorEnv(V80(), B, config=cfg, n_passthrough=0.2, seed=5, device="cuda:0", pooled=False))
     obs, infos = env.reset(seed=5)
     v = env.env.venv
     tmax = v.time_max.copy()
@@ -217,3 +218,60 @@ def test_step_host_equals_step(built_lib):
     with pytest.raises(ValueError):
         b.step_host(np.zeros((B, T + 1), dtype=np.float32))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("multi", [False, True])
+def test_device_pool_autoreset_without_the_host(built_lib, multi):
+    """DevicePooledVecEnv (wg_pool_*): finished episodes are paired with ready spares and replaced on the device; a
+    swapped-in env is exactly a freshly reset env on the conditions the device drew for it; the finished episode's
+    last observation is kept; nothing is read back by the adapter.  Single- and multi-agent observation layouts."""
+    import torch
+    from windgym_b200 import DevicePooledVecEnv, GymVectorEnv, V80, VecWindFarmEnv
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    B, T, R = 6, 2, 6
+    env = GymVectorEnv(V80(), B, config=cfg, n_passthrough=0.2, seed=9, device="cuda:0", as_torch=True, reserve=R,
+                       refill_every=2, multi_agent=multi)
+    pool = env.venv
+    assert isinstance(pool, DevicePooledVecEnv) and pool.inner.n_envs == B + R
+    obs, infos = env.reset(seed=9)
+    oshape = (B, T, 2) if multi else (B, 4)
+    assert tuple(obs.shape) == oshape and tuple(env.single_observation_space.shape) == oshape[1:]
+    torch.cuda.synchronize()
+    assert (pool.inner.state["pool_status"][:B] == 0).all()
+    zeros = torch.zeros((B, T), dtype=torch.float32, device="cuda:0")
+    checked, n_swapped, prev_obs = 0, 0, obs.clone()
+    for k in range(70):
+        ws_before = pool.ws.clone()
+        ts_before = pool.state["timestep"].clone()
+        obs, r, term, trunc, infos = env.step(zeros)
+        torch.cuda.synchronize()
+        tr = trunc.cpu().numpy().astype(bool)
+        assert tuple(obs.shape) == oshape and bool(torch.isfinite(obs).all()) and not bool(term.any())
+        ts = pool.state["timestep"].cpu().numpy()
+        assert (ts[tr] == 0).all() and (ts[~tr] == ts_before.cpu().numpy()[~tr] + 1).all()
+        if tr.any():
+            n_swapped += int(tr.sum())
+            wsn, wsb = pool.ws.cpu().numpy(), ws_before.cpu().numpy()
+            assert (wsn[tr] != wsb[tr]).all() and (wsn[~tr] == wsb[~tr]).all()
+            assert (wsn >= 7).all() and (wsn <= 15).all()
+            fo = infos["final_observation"]
+            assert np.array_equal(infos["_final_observation"].cpu().numpy(), tr)
+            assert bool(torch.isfinite(fo[trunc.bool()]).all()) and not torch.equal(fo[trunc.bool()], obs[trunc.bool()])
+            if checked < 3:   # the swapped-in state is a genuine reset onto the conditions the device drew
+                fresh = VecWindFarmEnv(V80(), B, config=cfg, n_passthrough=0.2, device="cuda:0", multi_agent=multi)
+                f_obs, _ = fresh.reset(wind=(pool.ws.cpu().numpy().astype(np.float64), pool.ti.cpu().numpy().astype(np.float64),
+                                             pool.wd.cpu().numpy().astype(np.float64)),
+                                       yaw0=pool.state["yaw"][:, 0].cpu().numpy())
+                assert np.array_equal(f_obs.cpu().numpy()[tr], obs.cpu().numpy()[tr])
+                for key in ("count", "head", "n_step", "power", "time_max"):
+                    a, b = fresh.state[key].cpu().numpy(), pool.state[key].cpu().numpy()
+                    assert np.array_equal(a[tr], b[tr]), key
+                fresh.close()
+                checked += 1
+        prev_obs = obs.clone()
+    pool.check_flags()
+    st = pool.stats
+    assert checked == 3 and st["swapped"] == n_swapped >= 10 and st["refilled"] >= st["swapped"] and st["refill_calls"] >= 30
+    status = pool.inner.state["pool_status"].cpu().numpy()
+    assert (status[:B] == 0).all() and set(status[B:].tolist()) <= {1, 2, 3, 4}
+    env.close()

@@ -118,3 +118,38 @@ def test_facade_with_mann_box_runs_and_meanders(built_lib):
     img_env = env.fs.get_windspeed(type("V", (), dict(x=np.linspace(-400, 800, 40), y=np.linspace(-200, 200, 30), z=70.0))())
     assert np.std(img_env[2]) > 0                                       # w' present in the rendered field
     env.close()
+
+
+def test_brick_layout_is_bit_identical_to_the_compact_box(built_lib, monkeypatch):
+    """Large turbulence boxes are re-laid as 64-byte bricks (8 trilinear corners per cell, wg_set_turbulence) so that a
+    wake-centre sample is one aligned read: same values, same interpolation order -> the same bits as gathering the 8
+    corners from the caller's compact layout.  Forced on the small test box here."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    _, box = _boxes()
+    cfg = small_config(2, 2, reward="Power_avg", action="wind")
+    B, T, steps = 8, 4, 12
+    rng = np.random.default_rng(5)
+    ws, ti, wd = rng.uniform(8, 13, B), rng.uniform(0.05, 0.12, B), rng.uniform(262, 278, B)
+    yaw0 = rng.uniform(-15, 15, (B, T))
+    off = rng.uniform(0, 1, (B, 3)) * (np.array(N) * np.array(D3))
+    off[0] = (np.array(N) * np.array(D3)) - 1e-3          # an env at the periodic seam of the box
+    acts = rng.uniform(-1, 1, (steps, B, T)).astype(np.float32)
+
+    def run():
+        env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="MannFixed", turb_box=box)
+        env.reset(wind=(ws, ti, wd), yaw0=yaw0, turb_offset=off)
+        out = []
+        for a in acts:
+            o, r, _, _, info = env.step(torch.as_tensor(a))
+            out.append((o.cpu().numpy().copy(), info["Power pr turbine agent"].cpu().numpy().copy(),
+                        env.state["pmut"].cpu().numpy().copy()))
+        env.check_flags(); env.close()
+        return out
+    monkeypatch.setenv("WG_NO_BRICKS", "1")
+    compact = run()
+    monkeypatch.delenv("WG_NO_BRICKS")
+    monkeypatch.setenv("WG_FORCE_BRICKS", "1")
+    bricks = run()
+    for (o1, p1, s1), (o2, p2, s2) in zip(compact, bricks):
+        assert np.array_equal(o1, o2) and np.array_equal(p1, p2) and np.array_equal(s1, s2)

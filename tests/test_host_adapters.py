@@ -175,3 +175,43 @@ def test_eval_dataset_roundtrip_and_agent_eval(tmp_path):
         eval_batched(FakeVecEnv(3), ConstantAgent([0, 0, 0]), [8.0, 9.0], t_sim=2)
     with pytest.raises(NotImplementedError):
         eval_batched(FakeVecEnv(1), ConstantAgent([0, 0, 0]), turbboxes=["box7"], t_sim=2)
+
+
+def _ppo_golden():
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ppo_golden.npz"))
+    sd = {k[3:]: torch.as_tensor(z[k]) for k in z.files if k.startswith("sd/")}
+    return z, sd
+
+
+def test_shipped_ppo_agent_actions_match_the_numpy_evaluation():
+    """The reference ships examples/PPO_2975000.zip (SB3 MlpPolicy 8 -> 64 -> 64 -> 4).  Its actor weights and its
+    deterministic actions on 67 fixed observations (evaluated with plain numpy by tests/golden/make_golden.py:make_ppo)
+    are committed; SB3MlpPolicy must reproduce them."""
+    z, sd = _ppo_golden()
+    pol = SB3MlpPolicy.from_state_dict(sd)
+    assert [m.in_features for m in pol.policy_net if hasattr(m, "in_features")] == [8, 64] and pol.action_net.out_features == 4
+    got = pol.predict_batch(torch.as_tensor(z["obs"])).numpy()
+    assert got.shape == (67, 4) and np.abs(got - z["actions"]).max() < 2e-6
+    assert np.abs(z["actions"]).max() <= 1.0 and np.std(z["actions"]) > 0.05      # a trained policy, not a constant
+
+
+@pytest.mark.reference
+def test_shipped_ppo_zip_loads_with_from_zip():
+    """SB3MlpPolicy.from_zip on the reference's own model file (build container only)."""
+    import os
+    path = "/root/reference/examples/PPO_2975000.zip"
+    if not os.path.isfile(path):
+        pytest.skip("reference checkout not present")
+    z, sd = _ppo_golden()
+    pol = SB3MlpPolicy.from_zip(path)
+    for k, v in sd.items():
+        own = "policy_net." + k[len("mlp_extractor.policy_net."):] if k.startswith("mlp_extractor.") else k
+        assert torch.equal(pol.state_dict()[own], v), k
+    assert np.abs(pol.predict_batch(torch.as_tensor(z["obs"])).numpy() - z["actions"]).max() < 2e-6
+    with pytest.raises(ValueError):
+        import tempfile, zipfile
+        with tempfile.NamedTemporaryFile(suffix=".zip") as f:
+            with zipfile.ZipFile(f.name, "w") as zz:
+                zz.writestr("data", "{}")
+            SB3MlpPolicy.from_zip(f.name)

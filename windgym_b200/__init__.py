@@ -16,9 +16,9 @@ def __getattr__(name):  # torch-dependent classes are imported lazily so `import
     if name in ("WindFarmEnv", "FarmEval", "WindFarmEnvMulti"):
         from . import envs
         return getattr(envs, name)
-    if name == "PooledVecEnv":
-        from .pool import PooledVecEnv
-        return PooledVecEnv
+    if name in ("PooledVecEnv", "DevicePooledVecEnv"):
+        from . import pool
+        return getattr(pool, name)
     if name in ("GymVectorEnv", "SB3VecEnv", "RecordEpisodeVals"):
         from . import vector
         return getattr(vector, name)

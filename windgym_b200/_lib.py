@@ -49,6 +49,13 @@ class ResetArgs(C.Structure):
                 ("tb_scale", C.c_void_p)]
 
 
+class PoolDraw(C.Structure):
+    _fields_ = [("ws_min", C.c_double), ("ws_max", C.c_double), ("ti_min", C.c_double), ("ti_max", C.c_double),
+                ("wd_min", C.c_double), ("wd_max", C.c_double), ("yaw_start", C.c_double), ("n_passthrough", C.c_double),
+                ("tb_std_u", C.c_double), ("yaw_const", C.c_float), ("yaw_random", C.c_int32), ("eval_mode", C.c_int32),
+                ("seed", C.c_uint64)]
+
+
 # every symbol include/windgym_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "wg_create": (C.c_int, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
@@ -70,6 +77,10 @@ SYMBOLS = {
                                       C.c_void_p, C.c_void_p]),
     "wg_set_active": (C.c_int, [C.c_void_p, C.c_int32]),
     "wg_copy_envs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "wg_pool_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
+    "wg_pool_refill": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PoolDraw), C.c_void_p, C.c_int32, C.c_void_p]),
+    "wg_pool_swap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_pool_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "wg_set_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_float]),
     "wg_set_added_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float,

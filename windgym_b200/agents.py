@@ -137,6 +137,19 @@ class SB3MlpPolicy(torch.nn.Module):
         """``policy.pth`` extracted from an SB3 zip (plain ``torch.load(weights_only=True)``, SURVEY.md section 2 #16)."""
         return cls.from_state_dict(torch.load(path, map_location=device, weights_only=True)).to(device)
 
+    @classmethod
+    def from_zip(cls, path, device="cpu"):
+        """The model file stable-baselines3 writes (``PPO.save`` -> ``*.zip`` holding ``policy.pth``; the reference ships
+        ``examples/PPO_2975000.zip`` and loads it with ``PPO.load``, examples/Example 3 .. / AgentEval usage): read
+        ``policy.pth`` straight out of the archive, no stable-baselines3 needed."""
+        import io
+        import zipfile
+        with zipfile.ZipFile(path) as z:
+            if "policy.pth" not in z.namelist():
+                raise ValueError(f"{path}: no policy.pth inside (not a stable-baselines3 model zip)")
+            buf = io.BytesIO(z.read("policy.pth"))
+        return cls.from_state_dict(torch.load(buf, map_location=device, weights_only=True)).to(device)
+
     @torch.no_grad()
     def predict_batch(self, obs, env=None, deterministic=True):
         mean = self.action_net(self.policy_net(obs.to(self.log_std.device, torch.float32)))

@@ -70,6 +70,7 @@ struct wg_handle {
   int n_work = 0;                     // entries of the current table
   int tail_units = 0, tail_parts = 1; // WG_TAIL_UNITS / WG_TAIL_PARTS in the environment (A/B measurements)
   bool use_split = true;              // WG_NO_SPLIT=1: never cut a farm into parts
+  bool use_pdl = true;                // WG_NO_PDL=1: plain stream order between the flow and the finish kernel
   // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
   // number, and the pinned host ranges already identified (host base, device alias, bytes)
   unsigned* flag_host = nullptr;
@@ -82,6 +83,9 @@ struct wg_handle {
   // L2 residency of the turbulence box: streams that already carry the access-policy window
   std::vector<cudaStream_t> policy_streams;
   size_t tb_lp_bytes = 0;
+  float4* d_lp8 = nullptr;            // library-owned brick copy of the low-pass box (large boxes only)
+  bool use_bricks = true;             // WG_NO_BRICKS=1: always gather from the caller's lp layout
+  bool force_bricks = false;          // WG_FORCE_BRICKS=1: bricks whatever the box size (tests)
 };
 
 namespace {
@@ -111,7 +115,7 @@ Tp* at(void* base, const wg_handle* h, const char* name) {
 // launching stream (measured on cfg 2 + 1024x128x32 box: 0.78 -> 0.64 ms per launch; per-load evict_last hints were
 // slower than plain loads).  Best effort: failures leave the default policy.
 void pin_turbulence_in_l2(wg_handle* h, cudaStream_t s) {
-  if (!h->dev.tb_lp) return;
+  if (!h->dev.tb_lp || h->dev.tb_lp8) return;  // bricks: the box is too large to stay in L2 anyway
   for (cudaStream_t t : h->policy_streams)
     if (t == s) return;
   h->policy_streams.push_back(s);
@@ -415,6 +419,23 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "part_arrive", 1, {B, F});
   h->work_cap = std::max(B * F * 2, 2048);
   add_field(h, "work", 1, {h->work_cap, 2});
+  // device-side spare pool (wg_pool_*): slot status, RNG generation, the step's swap list, counters, refill masks and
+  // the reset arguments of the slots being refilled
+  add_field(h, "pool_status", 1, {B});
+  add_field(h, "pool_gen", 1, {B});
+  add_field(h, "pool_swap", 1, {2 * WG_POOL_MAX_SWAP + 2});
+  add_field(h, "pool_stats", 1, {16});
+  add_field(h, "pool_masks", 1, {WG_POOL_MASKS, (B + 3) / 4});
+  for (const char* n : {"pool_ws", "pool_ti", "pool_ti_flow", "pool_wd", "pool_rated", "pool_tb_scale"}) add_field(h, n, 0, {B});
+  add_field(h, "pool_yaw0", 0, {B, T});
+  add_field(h, "pool_tb_off", 0, {B, 3});
+  for (const char* n : {"pool_k_emit", "pool_t_dev", "pool_time_max"}) add_field(h, n, 1, {B});
+  const char* no_br = getenv("WG_NO_BRICKS");
+  h->use_bricks = !(no_br && no_br[0] == '1');
+  const char* f_br = getenv("WG_FORCE_BRICKS");
+  h->force_bricks = f_br && f_br[0] == '1';
+  const char* no_pdl = getenv("WG_NO_PDL");
+  h->use_pdl = !(no_pdl && no_pdl[0] == '1');
   const char* no_zc = getenv("WG_NO_ZEROCOPY");
   h->use_zero_copy = !(no_zc && no_zc[0] == '1');
   const char* no_split = getenv("WG_NO_SPLIT");
@@ -436,6 +457,7 @@ void wg_destroy(wg_handle* h) {
   cudaFree(h->d_tab_ws); cudaFree(h->d_tab_p); cudaFree(h->d_tab_ct); cudaFree(h->d_x); cudaFree(h->d_y);
   cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc); cudaFree(h->d_copy);
   cudaFree(h->d_done_count);
+  cudaFree(h->d_lp8);
   if (h->flag_host) cudaFreeHost(h->flag_host);
   delete h;
 }
@@ -492,23 +514,15 @@ int wg_flow_steps(wg_handle* h, void* state, int32_t n_steps, void* cuda_stream)
   return WG_OK;
 }
 
-int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, void* cuda_stream) {
-  if (!h || !state || !args || !obs) return fail(WG_ERR_INVALID, "wg_reset: null argument");
-  if (!args->ws || !args->ti_flow || !args->wd || !args->yaw0 || !args->rated_power || !args->k_emit ||
-      !args->t_developed || !args->time_max)
-    return fail(WG_ERR_INVALID, "wg_reset: every per-env input array is required");
-  cudaStream_t s = (cudaStream_t)cuda_stream;
+// WindFarmEnv.reset for the masked envs of the slot range [b0, b0 + nb)
+static int reset_impl(wg_handle* h, void* state, const wg::ResetDevArgs& ra, float* obs, cudaStream_t s, int b0, int nb) {
   pin_turbulence_in_l2(h, s);
-  h->order_state = nullptr;
   wg::Dev d = bind(h, state);
-  if (h->dev.tb_raw && (!args->tb_offset || !args->tb_scale))
-    return fail(WG_ERR_INVALID, "wg_reset: a handle with a turbulence box needs tb_offset and tb_scale");
-  wg::ResetDevArgs ra{args->mask, args->ws, args->ti_flow, args->wd, args->yaw0, args->rated_power,
-                      args->k_emit, args->t_developed, args->time_max, args->tb_offset, args->tb_scale};
+  d.b0 = b0; d.Bg = nb;
   WG_LAUNCH(wg::launch_reset_init(d, ra, s), "wg_reset_init_kernel");
   // fs.run(t_developed) for the agent farm and the baseline farm (Wind_Farm_Env.py:734, :782)
   wg::FlowArgs spin{};
-  spin.mode = wg::FLOW_SPIN; spin.mask = args->mask; spin.farm_mask = (1 << d.F) - 1;
+  spin.mode = wg::FLOW_SPIN; spin.mask = ra.mask; spin.farm_mask = (1 << d.F) - 1;
   WG_LAUNCH(wg::launch_flow(d, spin, s), "wg_flow_kernel(spin-up)");
   // measurement fill: steps_on_reset env steps for the agent farm (:737-766), hist_max for the baseline farm,
   // whose controller stays off during the fill (:784-796)
@@ -516,17 +530,30 @@ int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, v
   for (int i = 0; i < std::max(n_agent, n_base); ++i) {
     const int fm = (i < n_agent ? 1 : 0) | (i < n_base ? 2 : 0);
     wg::FlowArgs fa{};
-    fa.mode = wg::FLOW_STEP; fa.mask = args->mask; fa.farm_mask = fm;
+    fa.mode = wg::FLOW_STEP; fa.mask = ra.mask; fa.farm_mask = fm;
     WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(fill)");
     wg::FinishArgs fin{};
-    fin.mask = args->mask;
+    fin.mask = ra.mask;
     fin.flags = ((fm & 1) ? (wg::FIN_PUSH_MES | wg::FIN_PUSH_FP) : 0) | ((fm & 2) ? wg::FIN_PUSH_BP : 0);
     WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(fill)");
   }
   wg::FinishArgs fin{};
-  fin.mask = args->mask; fin.flags = wg::FIN_OBS; fin.obs = obs;
+  fin.mask = ra.mask; fin.flags = wg::FIN_OBS; fin.obs = obs;
   WG_LAUNCH(wg::launch_finish(d, fin, s), "wg_finish_kernel(obs)");
   return WG_OK;
+}
+
+int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, void* cuda_stream) {
+  if (!h || !state || !args || !obs) return fail(WG_ERR_INVALID, "wg_reset: null argument");
+  if (!args->ws || !args->ti_flow || !args->wd || !args->yaw0 || !args->rated_power || !args->k_emit ||
+      !args->t_developed || !args->time_max)
+    return fail(WG_ERR_INVALID, "wg_reset: every per-env input array is required");
+  if (h->dev.tb_raw && (!args->tb_offset || !args->tb_scale))
+    return fail(WG_ERR_INVALID, "wg_reset: a handle with a turbulence box needs tb_offset and tb_scale");
+  h->order_state = nullptr;
+  wg::ResetDevArgs ra{args->mask, args->ws, args->ti_flow, args->wd, args->yaw0, args->rated_power,
+                      args->k_emit, args->t_developed, args->time_max, args->tb_offset, args->tb_scale};
+  return reset_impl(h, state, ra, obs, (cudaStream_t)cuda_stream, 0, h->cfg.n_envs);
 }
 
 // host_out: optional mapped host copies of the results + completion flag (wg_step_host's zero-copy path)
@@ -578,13 +605,16 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   }
   wg::FlowArgs fa{};
   fa.mode = wg::FLOW_STEP; fa.actions = actions; fa.farm_mask = (1 << d.F) - 1; fa.controller_on = 1;
-  if (by_table) { fa.work = d.work; fa.n_work = h->n_work; }
+  // fewer farms than CTA slots: overlap the finish kernel's launch + staging with the flow grid's tail (PDL)
+  const bool pdl = by_table && h->use_pdl && d.Bg * d.F < h->slots && !h->profiling;
+  if (by_table) { fa.work = d.work; fa.n_work = h->n_work; fa.pdl_trigger = pdl ? 1 : 0; }
   else fa.order = h->use_order ? d.order : nullptr;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
   if (ev) cudaEventRecord(ev[1], s);
   wg::FinishArgs fin{};
   fin.flags = wg::FIN_PUSH_MES | wg::FIN_PUSH_FP | (d.F > 1 ? wg::FIN_PUSH_BP : 0) | wg::FIN_OBS | wg::FIN_REWARD;
   fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
+  fin.pdl = pdl ? 1 : 0;
   if (host_out) {
     fin.obs_h = host_out->obs_h; fin.reward_h = host_out->reward_h; fin.truncated_h = host_out->truncated_h;
     fin.done_count = host_out->done_count; fin.done_flag = host_out->done_flag; fin.seq = host_out->seq;
@@ -721,7 +751,8 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   if (!h) return fail(WG_ERR_INVALID, "wg_set_turbulence: null argument");
   wg::Dev& d = h->dev;
   if (!raw_uvw0 && !lp_vw) {  // back to uniform inflow
-    d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr;
+    d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr; d.tb_lp8 = nullptr;
+    cudaFree(h->d_lp8); h->d_lp8 = nullptr;
     h->slots = 0; h->order_state = nullptr;
     return WG_OK;
   }
@@ -739,6 +770,27 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   h->tb_lp_bytes = (size_t)nx * ny * nz * sizeof(float2);
   h->policy_streams.clear();
   h->slots = 0; h->order_state = nullptr;  // another kernel variant: resident-CTA count and work table are stale
+  // The low-pass layout is re-laid as 64-byte bricks (8 trilinear corners per cell, 8x the memory -- HBM is
+  // plentiful): one aligned read per wake-centre sample instead of 4-8 scattered 32-byte sectors.  Measured on cfg 2:
+  // reference box 2048x512x64 1.39 -> 0.635 ms per launch; even the reduced test box (whose compact layout fits the
+  // persisting-L2 window of pin_turbulence_in_l2) 0.677 -> 0.608 ms.  The compact layout is the fallback when the
+  // bricks do not fit in memory (and WG_NO_BRICKS=1).
+  cudaFree(h->d_lp8);
+  h->d_lp8 = nullptr; d.tb_lp8 = nullptr;
+  int devid = 0, max_persist = 0;
+  cudaGetDevice(&devid);
+  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, devid);
+  (void)max_persist;
+  if (h->use_bricks) {
+    if (cudaMalloc(&h->d_lp8, h->tb_lp_bytes * 8) == cudaSuccess) {
+      cudaError_t e = wg::launch_bricks(d.tb_lp, h->d_lp8, nx, ny, nz, 0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+      if (e != cudaSuccess) return cuda_fail(e, "wg_set_turbulence: brick layout");
+      d.tb_lp8 = h->d_lp8;
+    } else {
+      cudaGetLastError();  // not enough memory for the bricks: keep gathering from the compact layout
+    }
+  }
   return WG_OK;
 }
 
@@ -780,6 +832,90 @@ int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* d
   WG_LAUNCH(wg::launch_copy_envs(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, src, dst, n,
                                  (cudaStream_t)cuda_stream),
             "wg_copy_envs_kernel");
+  return WG_OK;
+}
+
+static wg::PoolDev bind_pool(const wg_handle* h, void* state) {
+  wg::PoolDev p{};
+  p.status = at<int>(state, h, "pool_status");
+  p.gen = at<int>(state, h, "pool_gen");
+  p.swap = at<int>(state, h, "pool_swap");
+  p.stats = at<unsigned long long>(state, h, "pool_stats");
+  p.masks = at<uint8_t>(state, h, "pool_masks");
+  p.ws = at<float>(state, h, "pool_ws"); p.ti = at<float>(state, h, "pool_ti");
+  p.ti_flow = at<float>(state, h, "pool_ti_flow"); p.wd = at<float>(state, h, "pool_wd");
+  p.rated = at<float>(state, h, "pool_rated"); p.tb_scale = at<float>(state, h, "pool_tb_scale");
+  p.yaw0 = at<float>(state, h, "pool_yaw0"); p.tb_off = at<float>(state, h, "pool_tb_off");
+  p.k_emit = at<int>(state, h, "pool_k_emit"); p.t_dev = at<int>(state, h, "pool_t_dev");
+  p.time_max = at<int>(state, h, "pool_time_max");
+  p.n_active = h->n_active; p.B = h->cfg.n_envs;
+  return p;
+}
+
+int wg_pool_init(wg_handle* h, void* state, int32_t n_active, void* cuda_stream) {
+  if (!h || !state) return fail(WG_ERR_INVALID, "wg_pool_init: null argument");
+  if (n_active < 1 || n_active >= h->cfg.n_envs)
+    return fail(WG_ERR_INVALID, "wg_pool_init: n_active must leave at least one spare slot (1 <= n_active < n_envs)");
+  h->n_active = n_active;
+  wg::PoolDev p = bind_pool(h, state);
+  std::vector<int> st((size_t)p.B, wg::POOL_ACTIVE);
+  for (int b = n_active; b < p.B; ++b) st[b] = wg::POOL_NEED;
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  cudaError_t e;
+  if ((e = cudaMemcpyAsync(p.status, st.data(), sizeof(int) * st.size(), cudaMemcpyHostToDevice, s)) != cudaSuccess ||
+      (e = cudaMemsetAsync(p.gen, 0, sizeof(int) * (size_t)p.B, s)) != cudaSuccess ||
+      (e = cudaMemsetAsync(p.swap, 0, sizeof(int) * (2 * WG_POOL_MAX_SWAP + 2), s)) != cudaSuccess ||
+      (e = cudaMemsetAsync(p.stats, 0, sizeof(int) * 16, s)) != cudaSuccess ||
+      (e = cudaStreamSynchronize(s)) != cudaSuccess)
+    return cuda_fail(e, "wg_pool_init");
+  return WG_OK;
+}
+
+int wg_pool_refill(wg_handle* h, void* state, const wg_pool_draw* draw, float* obs, int32_t mask_row, void* cuda_stream) {
+  if (!h || !state || !draw || !obs) return fail(WG_ERR_INVALID, "wg_pool_refill: null argument");
+  if (mask_row < 0 || mask_row >= WG_POOL_MASKS) return fail(WG_ERR_INVALID, "wg_pool_refill: mask_row out of range");
+  if (h->n_active >= h->cfg.n_envs) return fail(WG_ERR_INVALID, "wg_pool_refill: no spare slots (wg_pool_init first)");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  wg::Dev d = bind(h, state);
+  wg::PoolDev p = bind_pool(h, state);
+  wg::PoolDraw w{};
+  w.ws_min = draw->ws_min; w.ws_max = draw->ws_max; w.ti_min = draw->ti_min; w.ti_max = draw->ti_max;
+  w.wd_min = draw->wd_min; w.wd_max = draw->wd_max; w.yaw_start = draw->yaw_start; w.n_passthrough = draw->n_passthrough;
+  w.yaw_const = draw->yaw_const; w.yaw_random = draw->yaw_random; w.eval_mode = draw->eval_mode; w.seed = draw->seed;
+  if (h->dev.tb_raw) {
+    if (!(draw->tb_std_u > 0.0)) return fail(WG_ERR_INVALID, "wg_pool_refill: tb_std_u (std of the box's u) is required with a turbulence box");
+    for (int k = 0; k < 3; ++k) w.tb_len[k] = (double)h->dev.tb_n[k] / (double)h->dev.tb_inv_d[k];
+    w.tb_inv_std = 1.0 / draw->tb_std_u;
+  }
+  WG_LAUNCH(wg::launch_pool_claim(d, p, w, mask_row, s), "wg_pool_claim_kernel");
+  wg::ResetDevArgs ra{p.masks + (size_t)mask_row * p.B, p.ws, p.ti_flow, p.wd, p.yaw0, p.rated,
+                      p.k_emit, p.t_dev, p.time_max, p.tb_off, p.tb_scale};
+  const int rc = reset_impl(h, state, ra, obs, s, p.n_active, p.B - p.n_active);
+  if (rc != WG_OK) return rc;
+  WG_LAUNCH(wg::launch_pool_publish(p, mask_row, s), "wg_pool_publish_kernel");
+  return WG_OK;
+}
+
+int wg_pool_swap(wg_handle* h, void* state, const uint8_t* truncated, float* obs, uint8_t* swapped, float* final_obs,
+                 void* cuda_stream) {
+  if (!h || !state || !truncated || !obs || !swapped) return fail(WG_ERR_INVALID, "wg_pool_swap: null argument");
+  if (h->n_active >= h->cfg.n_envs) return fail(WG_ERR_INVALID, "wg_pool_swap: no spare slots (wg_pool_init first)");
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  wg::Dev d = bind(h, state);
+  wg::PoolDev p = bind_pool(h, state);
+  WG_LAUNCH(wg::launch_pool_swap(d, p, truncated, swapped, s), "wg_pool_swap_kernel");
+  WG_LAUNCH(wg::launch_pool_copy(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, p, obs, final_obs,
+                                 h->dev.obs_rows * h->dev.obs_dim, s),
+            "wg_pool_copy_kernel");
+  return WG_OK;
+}
+
+int wg_pool_stats(wg_handle* h, void* state, uint64_t out[8], void* cuda_stream) {
+  if (!h || !state || !out) return fail(WG_ERR_INVALID, "wg_pool_stats: null argument");
+  wg::PoolDev p = bind_pool(h, state);
+  cudaError_t e = cudaMemcpyAsync(out, p.stats, sizeof(uint64_t) * 8, cudaMemcpyDeviceToHost, (cudaStream_t)cuda_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)cuda_stream);
+  if (e != cudaSuccess) return cuda_fail(e, "wg_pool_stats");
   return WG_OK;
 }
 

@@ -99,8 +99,8 @@ __device__ __noinline__ float calc_ti(Get get, int L) {  // rare observation kin
 template <bool STAGE, bool LEAN>
 __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const Dev d, const FinishArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
-  const int b = blockIdx.x * WG_FIN_WARPS + warp;
-  if (b >= d.Bg) return;
+  const int b = d.b0 + blockIdx.x * WG_FIN_WARPS + warp;
+  if (b >= d.b0 + d.Bg) return;
   if (a.mask && !a.mask[b]) return;
   extern __shared__ __align__(16) float s_dyn[];
   __shared__ float s_vals[WG_FIN_WARPS][4][WG_MAX_T];
@@ -125,8 +125,13 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   // scalars of the env, loaded up front (used by the pushes and the reward at the end)
   int np = d.n_push[b];
   int nfp_tot = d.n_fp[b], nbp_tot = d.n_bp[b];
-  const float g_base_pow = d.base_pow_mean[b], g_rated = d.rated[b];
+  const float g_rated = d.rated[b];
   const int g_ts = d.timestep[b], g_tmax = d.time_max[b];
+  // Programmatic dependent launch behind the step's flow kernel: everything above (ring staging, env scalars -- none
+  // of it written by the flow kernel) ran while the flow grid was still draining; its results (substep means, baseline
+  // power, yaws) are read from here on.  Without the launch attribute the wait returns at once.
+  if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  const float g_base_pow = d.base_pow_mean[b];
   if (a.flags & (FIN_PUSH_MES | FIN_PUSH_FP))
     for (int t = lane; t < T; t += 32) {
       const float* src[4] = {a.in_ws, a.in_wd, a.in_yaw, a.in_power};
@@ -281,7 +286,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
 
 // WindFarmEnv.reset head (Wind_Farm_Env.py:689-732): wind conditions, rotated layout, clean flow + measurement state
 __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
-  const int b = blockIdx.x, tid = threadIdx.x, T = d.T;
+  const int b = d.b0 + blockIdx.x, tid = threadIdx.x, T = d.T;
   if (a.mask && !a.mask[b]) return;
   const double wdv = (double)a.wd[b];
   const double th = (270.0 - wdv) * 0.017453292519943295;
@@ -344,6 +349,16 @@ cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
       if (e != cudaSuccess) return e;
       configured = smem;
     }
+    if (a.pdl) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WG_FIN_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      return d.fin_lean ? cudaLaunchKernelEx(&cfg, wg_finish_kernel<true, true>, d, a)
+                        : cudaLaunchKernelEx(&cfg, wg_finish_kernel<true, false>, d, a);
+    }
     if (d.fin_lean) wg_finish_kernel<true, true><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
     else wg_finish_kernel<true, false><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
   } else {
@@ -353,7 +368,7 @@ cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s) {
-  wg_reset_init_kernel<<<d.B, 64, 0, s>>>(d, a);
+  wg_reset_init_kernel<<<d.Bg, 64, 0, s>>>(d, a);
   return cudaGetLastError();
 }
 
@@ -535,6 +550,194 @@ __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ l
 
 cudaError_t launch_plan(const Dev& d, const PlanArgs& p, cudaStream_t s) {
   wg_plan_kernel<<<1, 1024, 0, s>>>(d.load, d.Bg * d.F, p, d.work);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ device-side pool
+// Auto-reset without the host in the loop (reference: the env is reset by its caller right after a truncated step,
+// Wind_Farm_Env.py:1003-1025; reset = t_developed + fill flow steps, :722-766).  The envs [n_active, B) of the
+// allocation are spares.  Every step, on the stepping stream: wg_pool_swap_kernel pairs finished episodes with READY
+// spares and wg_pool_copy_kernel copies the spares' state over them.  Every few steps, on a background stream:
+// wg_pool_claim_kernel takes the spares that were consumed, draws new wind conditions for them (counter-based RNG),
+// the masked reset spins them up, wg_pool_publish_kernel marks them READY.  A spare travels
+//   NEED -> (claim) REFILLING -> (publish) READY -> (swap) PENDING -> (next step's swap, i.e. after the copy) NEED.
+__device__ __forceinline__ double pool_uniform(unsigned long long seed, int slot, int gen, int k) {
+  unsigned long long x = splitmix(seed ^ splitmix(((unsigned long long)(unsigned)slot << 32) | (unsigned)gen));
+  x = splitmix(x + 0x632BE59BD9B4E019ull * (unsigned long long)(k + 1));
+  return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+__global__ void __launch_bounds__(128) wg_pool_claim_kernel(const Dev d, const PoolDev p, const PoolDraw w, int mask_row) {
+  const int b = p.n_active + blockIdx.x, tid = threadIdx.x, T = d.T;
+  if (b >= p.B) return;
+  uint8_t* mask = p.masks + (size_t)mask_row * p.B;
+  __shared__ int s_take;
+  if (tid == 0) {
+    s_take = atomicCAS(&p.status[b], POOL_NEED, POOL_REFILLING) == POOL_NEED ? 1 : 0;
+    mask[b] = (uint8_t)s_take;
+  }
+  __syncthreads();
+  if (!s_take) return;
+  const int gen = p.gen[b];
+  // draw order of the reference: ws, ti, wd, then the yaw offsets (Wind_Farm_Env.py:564-568, :715)
+  const double ws = w.ws_min + (w.ws_max - w.ws_min) * pool_uniform(w.seed, b, gen, 0);
+  const double ti = w.ti_min + (w.ti_max - w.ti_min) * pool_uniform(w.seed, b, gen, 1);
+  const double wd = w.wd_min + (w.wd_max - w.wd_min) * pool_uniform(w.seed, b, gen, 2);
+  for (int t = tid; t < T; t += blockDim.x)
+    p.yaw0[b * T + t] = w.yaw_random ? (float)(-w.yaw_start + 2.0 * w.yaw_start * pool_uniform(w.seed, b, gen, 8 + t))
+                                     : w.yaw_const;
+  if (tid == 0) {
+    // integer decisions of the reset in fp64, as the reference makes them (:723-732; EnvConfig.reset_integers)
+    const double th = (270.0 - wd) * 0.017453292519943295, c = cos(th), sn = sin(th);
+    double mx = 0.0, my = 0.0;
+    for (int t = 0; t < T; ++t) { mx += d.x_pos[t]; my += d.y_pos[t]; }
+    mx /= T; my /= T;
+    double lo = 1e300, hi = -1e300;
+    for (int t = 0; t < T; ++t) {
+      const double xr = (d.x_pos[t] - mx) * c + (d.y_pos[t] - my) * sn;
+      lo = fmin(lo, xr); hi = fmax(hi, xr);
+    }
+    const double t_inflow = (hi - lo) / ws;
+    const long long t_dev = (long long)(t_inflow * 2.0);
+    p.t_dev[b] = (int)llrint((double)t_dev / (double)d.dt);
+    p.time_max[b] = w.eval_mode ? 9999999 : (int)(t_inflow * w.n_passthrough);
+    p.k_emit[b] = max(1, (int)ceil((double)d.d_particle * (double)d.D / (ws * (double)d.dt) - 1e-9));
+    p.ws[b] = (float)ws; p.ti[b] = (float)ti; p.wd[b] = (float)wd;
+    // turbine.power(ws): np.interp on the power table (Wind_Farm_Env.py:700)
+    const int n = d.n_tab;
+    double pw;
+    if (ws <= (double)d.tab_ws[0]) pw = d.tab_p[0];
+    else if (ws >= (double)d.tab_ws[n - 1]) pw = d.tab_p[n - 1];
+    else {
+      int k = 0;
+      while (k + 2 < n && (double)d.tab_ws[k + 1] <= ws) ++k;
+      const double x0 = d.tab_ws[k], x1 = d.tab_ws[k + 1];
+      pw = ((double)d.tab_p[k + 1] - (double)d.tab_p[k]) / (x1 - x0) * (ws - x0) + (double)d.tab_p[k];
+    }
+    p.rated[b] = (float)pw;
+    if (w.tb_inv_std > 0.0) {  // an env position inside the shared turbulence box, scale_TI factor TI U / std(u_box)
+      for (int k = 0; k < 3; ++k) p.tb_off[b * 3 + k] = (float)(w.tb_len[k] * pool_uniform(w.seed, b, gen, 4 + k));
+      p.tb_scale[b] = (float)(ti * ws * w.tb_inv_std);
+      p.ti_flow[b] = (float)ti;
+    } else {
+      for (int k = 0; k < 3; ++k) p.tb_off[b * 3 + k] = 0.f;
+      p.tb_scale[b] = 0.f;
+      p.ti_flow[b] = 0.f;  // turbtype "None": RandomTurbulence(ti = 0) (:661-665)
+    }
+    p.gen[b] = gen + 1;
+  }
+}
+
+__global__ void wg_pool_publish_kernel(const PoolDev p, int mask_row) {
+  const int b = p.n_active + blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  if (p.masks[(size_t)mask_row * p.B + b]) {
+    __threadfence();
+    atomicCAS(&p.status[b], POOL_REFILLING, POOL_READY);
+    atomicAdd(&p.stats[2], 1ull);
+  }
+}
+
+// One CTA.  (1) spares whose copy was issued in the previous step are free to be refilled; (2) ready spares and
+// finished episodes are collected in index order and paired; (3) swapped[b] = 1 for the envs that get a new episode
+// in this step -- an episode that finds no ready spare simply runs on and is paired in a later step.
+__global__ void __launch_bounds__(1024) wg_pool_swap_kernel(const Dev d, const PoolDev p, const uint8_t* __restrict__ truncated,
+                                                            uint8_t* __restrict__ swapped) {
+  __shared__ int scan[1024];
+  __shared__ int wsum[32];
+  __shared__ int s_src[WG_POOL_MAX_SWAP], s_dst[WG_POOL_MAX_SWAP];
+  const int tid = threadIdx.x;
+  // ordered compaction (block scan, not atomics): the k-th ready spare goes to the k-th finished env, run after run
+  int nsrc = 0, ndst = 0;
+  for (int base = p.n_active; base < p.B; base += 1024) {
+    const int b = base + tid;
+    int flag = 0;
+    if (b < p.B) {
+      int st = p.status[b];
+      if (st == POOL_PENDING) { p.status[b] = POOL_NEED; st = POOL_NEED; }
+      flag = st == POOL_READY;
+    }
+    scan[tid] = flag;
+    const int total = __syncthreads_count(flag);
+    plan_exclusive_scan(scan, wsum);
+    if (flag && nsrc + scan[tid] < WG_POOL_MAX_SWAP) s_src[nsrc + scan[tid]] = b;
+    nsrc += total;
+    __syncthreads();
+  }
+  for (int base = 0; base < p.n_active; base += 1024) {
+    const int b = base + tid;
+    int flag = 0;
+    if (b < p.n_active) { swapped[b] = 0; flag = truncated[b] != 0; }
+    scan[tid] = flag;
+    const int total = __syncthreads_count(flag);
+    plan_exclusive_scan(scan, wsum);
+    if (flag && ndst + scan[tid] < WG_POOL_MAX_SWAP) s_dst[ndst + scan[tid]] = b;
+    ndst += total;
+    __syncthreads();
+  }
+  const int n = min(min(nsrc, ndst), WG_POOL_MAX_SWAP);
+  if (tid < n) {
+    const int src = s_src[tid], dst = s_dst[tid];
+    p.status[src] = POOL_PENDING;
+    p.swap[tid] = src;
+    p.swap[WG_POOL_MAX_SWAP + tid] = dst;
+    swapped[dst] = 1;
+  }
+  if (tid == 0) {
+    p.swap[2 * WG_POOL_MAX_SWAP] = n;
+    if (n) atomicAdd(&p.stats[0], (unsigned long long)n);
+    if (ndst > n) atomicAdd(&p.stats[1], (unsigned long long)(ndst - n));
+  }
+}
+
+// Copy the paired spares over the finished envs: grid (chunks, WG_POOL_MAX_SWAP); pair k >= n: nothing to do.
+// The finished env's last observation is kept in final_obs (the "terminal observation" of the vector-env APIs), its
+// observation row then becomes the spare's reset observation.
+__global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __restrict__ state, const CopyField* __restrict__ fields,
+                                                           int n_fields, const PoolDev p, float* __restrict__ obs,
+                                                           float* __restrict__ final_obs, int obs_floats) {
+  const int k = blockIdx.y;
+  if (k >= p.swap[2 * WG_POOL_MAX_SWAP]) return;
+  const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
+  const unsigned nchunk = gridDim.x, chunk = blockIdx.x;
+  for (int fi = 0; fi < n_fields; ++fi) {
+    const CopyField f = fields[fi];
+    const size_t so = (size_t)src * f.per_env, dof = (size_t)dst * f.per_env;
+    for (unsigned r = 0; r < f.n_rep; ++r) {
+      unsigned char* base = state + f.offset + (size_t)r * f.rep_stride;
+      if ((f.per_env & 15u) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(base + so);
+        uint4* d4 = reinterpret_cast<uint4*>(base + dof);
+        for (unsigned i = chunk * blockDim.x + threadIdx.x; i < f.per_env / 16; i += nchunk * blockDim.x) d4[i] = s4[i];
+      } else {
+        const unsigned* s1 = reinterpret_cast<const unsigned*>(base + so);
+        unsigned* d1 = reinterpret_cast<unsigned*>(base + dof);
+        for (unsigned i = chunk * blockDim.x + threadIdx.x; i < f.per_env / 4; i += nchunk * blockDim.x) d1[i] = s1[i];
+      }
+    }
+  }
+  if (chunk == 0)
+    for (int i = threadIdx.x; i < obs_floats; i += blockDim.x) {
+      if (final_obs) final_obs[(size_t)dst * obs_floats + i] = obs[(size_t)dst * obs_floats + i];
+      obs[(size_t)dst * obs_floats + i] = obs[(size_t)src * obs_floats + i];
+    }
+}
+
+cudaError_t launch_pool_claim(const Dev& d, const PoolDev& p, const PoolDraw& w, int mask_row, cudaStream_t s) {
+  wg_pool_claim_kernel<<<p.B - p.n_active, 128, 0, s>>>(d, p, w, mask_row);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_publish(const PoolDev& p, int mask_row, cudaStream_t s) {
+  wg_pool_publish_kernel<<<(p.B - p.n_active + 255) / 256, 256, 0, s>>>(p, mask_row);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* truncated, uint8_t* swapped, cudaStream_t s) {
+  wg_pool_swap_kernel<<<1, 1024, 0, s>>>(d, p, truncated, swapped);
+  return cudaGetLastError();
+}
+cudaError_t launch_pool_copy(unsigned char* state, const CopyField* fields, int n_fields, const PoolDev& p, float* obs,
+                             float* final_obs, int obs_floats, cudaStream_t s) {
+  wg_pool_copy_kernel<<<dim3(32, WG_POOL_MAX_SWAP), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
   return cudaGetLastError();
 }
 

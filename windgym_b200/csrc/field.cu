@@ -78,4 +78,29 @@ cudaError_t launch_flow_field(const Dev& d, int b, int f, const float* px, const
   return cudaGetLastError();
 }
 
+// 64-byte bricks of the low-pass box: cell (i, j, k) <- its 8 periodic trilinear corners, in sample_lp's order
+// ((a, b) pairs as one float4 = corners c = 0, 1).  Run once when a box is attached.
+__global__ void __launch_bounds__(256) wg_brick_kernel(const float2* __restrict__ lp, float4* __restrict__ lp8, int nx,
+                                                       int ny, int nz) {
+  const size_t n = (size_t)nx * ny * nz;
+  for (size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(c % nz), j = (int)((c / nz) % ny), i = (int)(c / ((size_t)nz * ny));
+    const int i1 = i + 1 == nx ? 0 : i + 1, j1 = j + 1 == ny ? 0 : j + 1, k1 = k + 1 == nz ? 0 : k + 1;
+    const int ii[2] = {i, i1}, jj[2] = {j, j1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float2* row = lp + ((size_t)ii[a] * ny + jj[b]) * nz;
+        const float2 q0 = row[k], q1 = row[k1];
+        lp8[c * 4 + a * 2 + b] = make_float4(q0.x, q0.y, q1.x, q1.y);
+      }
+  }
+}
+
+cudaError_t launch_bricks(const float2* lp, float4* lp8, int nx, int ny, int nz, cudaStream_t s) {
+  wg_brick_kernel<<<148 * 16, 256, 0, s>>>(lp, lp8, nx, ny, nz);
+  return cudaGetLastError();
+}
+
 }  // namespace wg

@@ -542,7 +542,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #endif
 
 template <int TC, int TURB>
-__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) : 4)
+__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
     wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // rows must be 256-byte aligned (XOR addressing)
   typedef FlowShared<TC, TURB> Shared;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   } else {
     const int bi = F == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, f_blk = F == 2 ? (int)(blockIdx.x & 1) : 0;
     if (!((a.farm_mask >> f_blk) & 1)) return;  // needs no load: before the TMEM allocation
-    bf = (a.order ? a.order[bi] : bi) * F + f_blk;
+    bf = (d.b0 + (a.order ? a.order[bi] : bi)) * F + f_blk;
   }
   const int b = F == 2 ? bf >> 1 : bf, f = F == 2 ? bf & 1 : 0;  // F is 1 or 2
 #ifdef WG_TRACE
@@ -594,6 +594,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB == 2 ? 5 : 6) 
   // relinquish -- 0.5 us when it is the first instruction, 2.9 us behind the prologue's loads).  Nothing loaded from
   // memory may be needed before this point (the work-table entry is first used below).
   if (warp == 0) tmem_alloc(&sh.tmem_base);
+  if (a.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (bf < 0) {  // unused entry of the work table (CTA-uniform): give the columns back
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();

@@ -47,7 +47,8 @@ struct ObsDesc {
 struct Dev {
   // dims
   int B, T, F, P, S, n_tab;
-  int Bg;  // envs [0, Bg) are launched: the whole allocation B, or the active prefix for wg_step (wg_set_active)
+  int Bg;  // envs [b0, b0 + Bg) are launched: the whole allocation B, the active prefix for wg_step (wg_set_active),
+  int b0;  //   or the spare range of a background refill (wg_pool_refill)
   float dt, D, R, zh, d_particle;
   float yaw_min, yaw_max, yaw_step;
   int action_method, base_controller;
@@ -100,6 +101,9 @@ struct Dev {
   // ambient turbulence box shared by all envs of the handle (null: uniform inflow); per-env offset and scale
   const float4* tb_raw;   // [Nx,Ny,Nz] (u, v, w, 0)
   const float2* tb_lp;    // [Nx,Ny,Nz] (v, w) low-pass filtered in y, z: moves the wake centres
+  const float4* tb_lp8;   // [Nx,Ny,Nz][4] the same field as 64-byte BRICKS: cell (i,j,k) holds its 8 trilinear corners
+                          // (i+a, j+b, k+c), periodic -- one aligned 64-byte read per sample instead of 8 scattered
+                          // sectors; built by the library for boxes too large to stay in L2 (null: gather from tb_lp)
   int tb_n[3];
   float tb_inv_d[3], tb_inv_n[3], tb_len_x;
   float *tb_off;          // [B,3] position of the env inside the box [m]
@@ -121,6 +125,8 @@ struct FlowArgs {
   const int* order;     // optional permutation of [0, Bg): CTA group i works on env order[i] (longest first)
   const int2* work;     // optional work table (single-step launches only): CTA i works on part work[i]; replaces order
   int n_work;           // entries of the table = CTAs of the launch
+  int pdl_trigger;      // every CTA releases the dependent launch (the step's finish kernel) at its start: the batch
+                        // leaves CTA slots free, so the finish grid's launch and staging overlap the flow grid's tail
 };
 
 // how wg_plan_kernel cuts the farms of a step into CTAs
@@ -142,6 +148,32 @@ struct FinishArgs {
   unsigned* done_count;          // device counter of finished warps (back to 0 when the flag is written)
   volatile unsigned* done_flag;  // mapped host word
   unsigned seq;
+  int pdl;                       // launched as programmatic dependent of the flow kernel (griddepcontrol.wait inside)
+};
+
+// Device-side spare pool (wg_pool_*): status of every env slot
+enum PoolStatus { POOL_ACTIVE = 0, POOL_NEED = 1, POOL_REFILLING = 2, POOL_READY = 3, POOL_PENDING = 4 };
+#define WG_POOL_MAX_SWAP 64     // swaps per step (more finished episodes wait for the next step)
+#define WG_POOL_MASKS 8         // refills in flight (one mask row each)
+
+struct PoolDev {
+  int* status;          // [B]   PoolStatus
+  int* gen;             // [B]   refills of the slot so far (RNG counter)
+  int* swap;            // [2 * WG_POOL_MAX_SWAP + 1]  src[], dst[], n of the current step
+  unsigned long long* stats;  // [8] swapped, deferred (finished episodes that found no ready spare), refilled
+  uint8_t* masks;       // [WG_POOL_MASKS, B]
+  // reset arguments of the slots being refilled (the arrays wg_reset takes, drawn on the device)
+  float *ws, *ti, *ti_flow, *wd, *yaw0, *rated, *tb_off, *tb_scale;
+  int *k_emit, *t_dev, *time_max;
+  int n_active, B;
+};
+
+struct PoolDraw {       // condition sampling of wg_pool_refill (EnvConfig on the host side)
+  double ws_min, ws_max, ti_min, ti_max, wd_min, wd_max, yaw_start, n_passthrough;
+  double tb_len[3], tb_inv_std;   // turbulence box extent [m] and 1 / std(u_box); tb_inv_std = 0: no box
+  float yaw_const;
+  int yaw_random, eval_mode;
+  unsigned long long seed;
 };
 
 struct ResetDevArgs {
@@ -200,6 +232,21 @@ __device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, floa
                                             float scale) {
   const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
   float v = 0.f, w = 0.f;
+  if (d.tb_lp8) {  // brick of cell (i0, j0, k0): corners in the order of the loops below, two per float4
+    const float4* p = d.tb_lp8 + (((size_t)b.i[0] * d.tb_n[1] + b.j[0]) * d.tb_n[2] + b.k[0]) * 4;
+    const float4 q[4] = {__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
+        const float4 c01 = q[a * 2 + bb];
+        const float w0 = wxy * (1.f - b.fz), w1 = wxy * b.fz;
+        v = fmaf(w0, c01.x, v); w = fmaf(w0, c01.y, w);
+        v = fmaf(w1, c01.z, v); w = fmaf(w1, c01.w, w);
+      }
+    return make_float2(v * scale, w * scale);
+  }
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -241,6 +288,10 @@ cudaError_t launch_flow(const Dev& d, const FlowArgs& a, cudaStream_t s);
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s);
 cudaError_t launch_order(const Dev& d, cudaStream_t s);
 cudaError_t launch_plan(const Dev& d, const PlanArgs& p, cudaStream_t s);
+cudaError_t launch_pool_claim(const Dev& d, const PoolDev& p, const PoolDraw& w, int mask_row, cudaStream_t s);
+cudaError_t launch_pool_publish(const PoolDev& p, int mask_row, cudaStream_t s);
+cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* truncated, uint8_t* swapped, cudaStream_t s);
+cudaError_t launch_bricks(const float2* lp, float4* lp8, int nx, int ny, int nz, cudaStream_t s);
 int flow_resident_ctas(const Dev& d);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
 // one state field as the env-copy kernel sees it: n_rep blocks of B envs, per_env bytes each
@@ -250,6 +301,8 @@ struct CopyField {
 };
 cudaError_t launch_copy_envs(unsigned char* state, const CopyField* fields, int n_fields, const int* src, const int* dst,
                              int n, cudaStream_t s);
+cudaError_t launch_pool_copy(unsigned char* state, const CopyField* fields, int n_fields, const PoolDev& p, float* obs,
+                             float* final_obs, int obs_floats, cudaStream_t s);
 cudaError_t launch_flow_field(const Dev& d, int b, int f, const float* px, const float* py, int n, float z, float* out,
                               cudaStream_t s);
 

@@ -189,3 +189,189 @@ class PooledVecEnv:
             m[idx[take:]] = True
             self.inner.reset(mask=m)
             self.stats["sync_resets"] += len(idx) - take
+
+
+class DevicePooledVecEnv:
+    """Auto-reset with the host out of the loop (``wg_pool_*`` in ``include/windgym_b200.h``).
+
+    Same idea as ``PooledVecEnv`` -- ``reserve`` spare env slots behind the ``n_envs`` active ones, spun up in the
+    background and copied over envs whose episode ended -- but every per-step decision is made on the device:
+    ``wg_pool_swap`` (two launches on the stepping stream) pairs finished episodes with ready spares and copies them,
+    ``wg_pool_refill`` (every ``refill_every`` steps, round robin over background streams) draws new wind conditions
+    for the consumed spares with a counter-based generator, runs the masked reset on them and marks them ready.  No
+    truncation flags are read back, no host-side bookkeeping per episode.  ``step()`` returns the new episode's first
+    observation for the swapped envs and ``truncated`` = the envs that were swapped in this step (an episode that
+    finds no ready spare runs on until one is; ``stats["deferred"]`` counts those env-steps); the finished episode's
+    last observation is in ``final_obs``.
+
+    Conditions come from the device generator (``seed``, slot, refill count) -- the same distributions as the
+    reference's draws (Wind_Farm_Env.py:557-568, :715), not numpy's PCG64 stream; the first episode of every active env
+    is a host-seeded ``VecWindFarmEnv.reset`` as before.  Works for the single-agent and the multi-agent observation
+    layout (obs [n_envs, obs] or [n_envs, T, obs])."""
+
+    device_autoreset = True
+
+    def __init__(self, turbine, n_envs, reserve=None, refill_every=8, n_streams=8, **env_kwargs):
+        import ctypes as C
+        from . import _lib
+        self._C, self._lib_mod = C, _lib
+        self.n_envs = int(n_envs)
+        # A spin-up takes ~20 ms whatever the batch size while episodes end at a rate of n_envs / episode length per
+        # step: the spares in flight are (finished episodes per second) x (spin-up latency) ~ 250-400 for the 4x4 farm
+        # at any batch size from 512 envs up; small batches are bounded by 4 spares per env
+        self.reserve = int(reserve) if reserve is not None else max(32, min(384, 4 * self.n_envs), self.n_envs // 8)
+        self.refill_every = max(1, int(refill_every))
+        self.inner = VecWindFarmEnv(turbine, self.n_envs + self.reserve, **env_kwargs)
+        v = self.inner
+        if v.sample_site is not None:
+            raise NotImplementedError("DevicePooledVecEnv draws uniform wind conditions on the device; use "
+                                      "PooledVecEnv (host-side draws) with sample_site")
+        self.device, self.ec, self.n_turb, self.obs_var = v.device, v.ec, v.n_turb, v.obs_var
+        self.obs_shape = (self.n_envs,) + tuple(v.obs_shape[1:])
+        self.Baseline_comp, self.n_farms = v.Baseline_comp, v.n_farms
+        self.yaw_min, self.yaw_max, self.yaw_step = v.yaw_min, v.yaw_max, v.yaw_step
+        self.x_pos, self.y_pos = v.x_pos, v.y_pos
+        self.lib = v.lib
+        n_streams = min(max(1, int(n_streams)), 8)          # one refill mask row per stream (WG_POOL_MASKS)
+        self._bgs = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self._n_refill = 0
+        self._steps = 0
+        B = self.n_envs
+        self.state = {k: (t[:, :B] if k == "pmut" else t[:B]) for k, t in v.state.items()
+                      if t.shape[0] == B + self.reserve or (k == "pmut" and t.shape[1] == B + self.reserve)}
+        self.terminated = v.terminated[:B]
+        self.swapped = torch.zeros(B + self.reserve, dtype=torch.uint8, device=self.device)
+        self._final = torch.zeros_like(v.obs)
+        self._ready = False
+
+    # ------------------------------------------------------------------------------------------ protocol
+    @property
+    def seed(self):
+        return self.inner.seed
+
+    @seed.setter
+    def seed(self, value):
+        self.inner.seed = value
+
+    @property
+    def ws(self):
+        return self.state["ws"]
+
+    @property
+    def ti(self):
+        return self.state["ti"]
+
+    @property
+    def wd(self):
+        return self.state["wd"]
+
+    @property
+    def time_max(self):
+        return self.state["time_max"]
+
+    @property
+    def obs(self):
+        return self.inner.obs[:self.n_envs]
+
+    @property
+    def final_obs(self):
+        """Last observation of the episodes that ended in the latest step (rows where ``truncated`` is set)."""
+        return self._final[:self.n_envs]
+
+    @property
+    def launch_count(self):
+        return self.inner.launch_count
+
+    @property
+    def stats(self):
+        """{"swapped", "deferred", "refilled"} so far (synchronises the device)."""
+        out = (self._C.c_uint64 * 8)()
+        self._lib_mod.check(self.lib.wg_pool_stats(self.inner._h, self.inner._step_ptrs[0], out, self.inner._stream()))
+        return {"swapped": int(out[0]), "deferred": int(out[1]), "refilled": int(out[2]), "refill_calls": self._n_refill}
+
+    def check_flags(self):
+        fl = self.state["flags"]
+        if bool((fl & 1).any()):
+            raise Exception("NaN Power")
+        if bool((fl & 2).any()):
+            raise self._lib_mod.WgError("wake particle chain overflow (p_cap too small)")
+
+    def _info(self):
+        d = getattr(self, "_info_views", None)
+        if d is None:
+            B, n_all = self.n_envs, self.n_envs + self.reserve
+            d = {k: (val[:B] if hasattr(val, "shape") and len(val.shape) and val.shape[0] == n_all else val)
+                 for k, val in self.inner._info().items()}
+            # the wind conditions live on the device: they change whenever a spare is swapped in
+            d["Wind speed Global"], d["Wind direction Global"], d["Turbulence intensity"] = self.ws, self.wd, self.ti
+            self._info_views = d
+        return dict(d)
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        self.inner.close()
+
+    # ------------------------------------------------------------------------------------------ reset / step
+    def _draw(self, seed):
+        ec, v = self.ec, self.inner
+        yc = 0.0
+        if ec.yaw_init_mode == "Defined":
+            yv = np.asarray(v.yaw_initial, dtype=np.float64).reshape(-1)
+            if yv.size != 1:
+                raise NotImplementedError("per-turbine 'Defined' yaw values need PooledVecEnv (host-side resets)")
+            yc = float(yv[0])
+        return self._lib_mod.PoolDraw(
+            ws_min=ec.ws_min, ws_max=ec.ws_max, ti_min=ec.TI_min, ti_max=ec.TI_max, wd_min=ec.wd_min, wd_max=ec.wd_max,
+            yaw_start=ec.yaw_start, n_passthrough=float(ec.n_passthrough),
+            tb_std_u=float(v.turb_box.std_u) if v.turb_box is not None else 0.0, yaw_const=yc,
+            yaw_random=int(ec.yaw_init_mode == "Random"), eval_mode=int(bool(ec.eval_mode)),
+            seed=int(0 if seed is None else seed) & 0xFFFFFFFFFFFFFFFF)
+
+    def reset(self, seed=None, mask=None, wind=None, yaw0=None):
+        """``mask=None``: reset every active env (host-seeded, like ``VecWindFarmEnv.reset``) and start preparing the
+        spares.  ``mask`` ([n_envs] bool): synchronous masked reset of those envs (the pool itself never needs it)."""
+        v, B, R = self.inner, self.n_envs, self.reserve
+        torch.cuda.synchronize(self.device)                     # no background work may touch the slots we reuse
+        m = np.zeros(B + R, dtype=bool)
+        if mask is None:
+            m[:B] = True
+        else:
+            m[:B] = np.asarray(mask, dtype=bool)[:B]
+        if wind is not None:
+            wind = tuple(np.concatenate([np.broadcast_to(np.asarray(w, dtype=np.float64), (B,)), np.zeros(R)]) for w in wind)
+        if yaw0 is not None:
+            yaw0 = np.concatenate([np.broadcast_to(np.asarray(yaw0, dtype=np.float64), (B, self.n_turb)),
+                                   np.zeros((R, self.n_turb))])
+        if seed is not None:
+            v.seed, v._episode = seed, 0
+        v.reset(seed=seed, mask=m, wind=wind, yaw0=yaw0)
+        if mask is None:
+            self._lib_mod.check(self.lib.wg_pool_init(v._h, v._step_ptrs[0], B, v._stream()))
+            v.n_active = B
+            v._n_act_elems = B * self.n_turb * self.ec.act_var
+            self._draw_args = self._draw(v.seed)
+            self._steps, self._ready = 0, True
+            self._refill()                                       # all spares: one batched spin-up
+        return self.obs, self._info()
+
+    def _refill(self):
+        k = self._n_refill % len(self._bgs)
+        bg = self._bgs[k]
+        v = self.inner
+        self._lib_mod.check(self.lib.wg_pool_refill(v._h, v._step_ptrs[0], self._C.byref(self._draw_args), v._step_ptrs[1],
+                                                    k, self._C.c_void_p(bg.cuda_stream)))
+        self._n_refill += 1
+
+    def step(self, actions):
+        if not self._ready:
+            raise RuntimeError("reset() must be called before step()")
+        v, B = self.inner, self.n_envs
+        obs, rew, term, trunc, _ = v.step(actions)
+        rc = self.lib.wg_pool_swap(v._h, v._step_ptrs[0], v._step_ptrs[3], v._step_ptrs[1], self.swapped.data_ptr(),
+                                   self._final.data_ptr(), v._stream())
+        if rc != 0:
+            self._lib_mod.check(rc)
+        self._steps += 1
+        if self._steps % self.refill_every == 0:
+            self._refill()
+        return obs[:B], rew[:B], term[:B], self.swapped[:B], self._info()

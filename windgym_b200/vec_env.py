@@ -38,6 +38,7 @@ class VecWindFarmEnv:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.WgError("VecWindFarmEnv runs on a CUDA device only (no CPU fallback)")
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.seed = seed
         self.sample_site = sample_site
         self._site_tables = None
@@ -75,6 +76,7 @@ class VecWindFarmEnv:
         self._host = None   # pinned host staging of step_host (allocated on first use)
         self.terminated = torch.zeros(self.n_envs, dtype=torch.bool, device=self.device)
         self._step_ptrs = (_ptr(self._state), _ptr(self.obs), _ptr(self.reward), _ptr(self.truncated))
+        self._n_act_elems = self.n_envs * self.n_turb * self.ec.act_var   # elements step() expects (active envs)
         # host copies of the per-env wind conditions of the current episode
         self.ws = np.zeros(self.n_envs); self.ti = np.zeros(self.n_envs); self.wd = np.zeros(self.n_envs)
         if reset_init:
@@ -184,7 +186,8 @@ class VecWindFarmEnv:
             pass
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        # raw handle of torch's current stream on this device (a plain C call: this sits on the per-step path)
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     @property
     def launch_count(self):
@@ -349,14 +352,15 @@ class VecWindFarmEnv:
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
             actions = actions.to(self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        n_act = getattr(self, "n_active", self.n_envs)
-        if actions.numel() != n_act * self.n_turb * self.ec.act_var:
-            raise ValueError(f"actions must have {n_act}x{self.n_turb * self.ec.act_var} elements")
+        if actions.numel() != self._n_act_elems:
+            raise ValueError(f"actions must have {self._n_act_elems // (self.n_turb * self.ec.act_var)}x"
+                             f"{self.n_turb * self.ec.act_var} elements")
         p = self._step_ptrs  # fixed buffers: the ctypes pointers are built once
-        rc = self.lib.wg_step(self._h, p[0], C.c_void_p(actions.data_ptr()), p[1], p[2], p[3], self._stream())
+        rc = self.lib.wg_step(self._h, p[0], actions.data_ptr(), p[1], p[2], p[3],
+                              torch._C._cuda_getCurrentRawStream(self._dev_index))
         if rc != 0:
             _lib.check(rc)
-        self._last_actions = actions
+        self._last_actions = actions   # keeps the tensor alive until the launch has consumed it
         return self.obs, self.reward, self.terminated, self.truncated, self._info()
 
     def step_host(self, actions):
@@ -380,9 +384,10 @@ class VecWindFarmEnv:
             _lib.check(self.lib.wg_result_bytes(self._h, C.byref(nb)))
             assert nb.value == self._out.numel(), "packed result buffer does not match the library's layout"
             self._host.update(act_ptr=_ptr(self._host["act_dev"]), out_ptr=_ptr(self._out),
-                              res_ptr=C.c_void_p(res.data_ptr()), n_res=C.c_size_t(nb.value))
+                              res_ptr=C.c_void_p(res.data_ptr()), n_res=C.c_size_t(nb.value),
+                              host_out=(self._host["obs"], self._host["reward"], self._host["truncated"]))
         h = self._host
-        n_need = getattr(self, "n_active", self.n_envs) * self.n_turb * self.ec.act_var
+        n_need = self._n_act_elems
         if (torch.is_tensor(actions) and actions.dtype == torch.float32 and actions.device.type == "cpu"
                 and actions.is_contiguous() and actions.numel() == n_need):
             a_ptr = actions.data_ptr()       # fast path: the caller's buffer goes to the C-ABI as it is
@@ -398,16 +403,17 @@ class VecWindFarmEnv:
         # kernels read the actions from and write the results to mapped host memory directly and the call returns when
         # the step's completion word arrives.  Pageable buffers: H2D copy, step, D2H copy, stream synchronise.
         rc = self.lib.wg_step_host(self._h, self._step_ptrs[0], a_ptr, h["act_ptr"], h["out_ptr"],
-                                   h["res_ptr"], h["n_res"], self._stream())
+                                   h["res_ptr"], h["n_res"], torch._C._cuda_getCurrentRawStream(self._dev_index))
         if rc != 0:
             _lib.check(rc)
-        return h["obs"], h["reward"], h["truncated"]
+        return h["host_out"]
 
     def set_active(self, n_active):
         """``wg_set_active``: ``step()`` advances only envs [0, n_active); the other slots are a spare pool
         (``windgym_b200.pool.PooledVecEnv``)."""
         _lib.check(self.lib.wg_set_active(self._h, int(n_active)))
         self.n_active = int(n_active)
+        self._n_act_elems = self.n_active * self.n_turb * self.ec.act_var
 
     def copy_envs(self, src, dst):
         """``wg_copy_envs``: complete per-env state of slot src[k] -> slot dst[k] (device copy on the current stream).

@@ -31,17 +31,29 @@ class _VectorBase:
     metadata = {"render_modes": [], "autoreset_mode": "same_step"}
     render_mode = None
 
-    def __init__(self, turbine=None, n_envs=1, venv=None, as_torch=False, auto_reset=True, **env_kwargs):
-        self.venv = venv if venv is not None else VecWindFarmEnv(turbine, n_envs, **env_kwargs)
+    def __init__(self, turbine=None, n_envs=1, venv=None, as_torch=False, auto_reset=True, pooled=None, **env_kwargs):
+        """``venv``: a ready ``VecWindFarmEnv`` / ``PooledVecEnv`` / ``DevicePooledVecEnv``.  Otherwise one is built:
+        with ``auto_reset`` (the default) a ``DevicePooledVecEnv`` -- finished episodes are replaced by pre-developed
+        spare envs on the device, no step ever waits for a spin-up; ``pooled=False`` (or ``auto_reset=False``) gives the
+        plain ``VecWindFarmEnv`` whose auto-reset is the masked in-step reset (exact reference RNG stream, but every
+        finished episode stalls the batch for its ~300-step spin-up)."""
+        if venv is None:
+            use_pool = auto_reset if pooled is None else bool(pooled)
+            if use_pool and env_kwargs.get("sample_site") is None:
+                from .pool import DevicePooledVecEnv
+                venv = DevicePooledVecEnv(turbine, n_envs, **env_kwargs)
+            else:
+                venv = VecWindFarmEnv(turbine, n_envs, **env_kwargs)
+        self.venv = venv
         v = self.venv
-        if len(v.obs_shape) != 2:
-            raise ValueError("vector adapters wrap the single-agent observation layout")
         self.num_envs = v.n_envs
         self.as_torch, self.auto_reset = as_torch, auto_reset
-        self.single_observation_space = Box(low=-1.0, high=1.0, shape=(v.obs_var,), dtype=np.float32)
-        self.single_action_space = Box(low=-1.0, high=1.0, shape=(v.n_turb,), dtype=np.float32)
-        self.observation_space = Box(low=-1.0, high=1.0, shape=(v.n_envs, v.obs_var), dtype=np.float32)
-        self.action_space = Box(low=-1.0, high=1.0, shape=(v.n_envs, v.n_turb), dtype=np.float32)
+        obs_one = tuple(v.obs_shape[1:])          # (obs_var,) single agent, (T, obs_var) multi agent
+        n_act = v.n_turb * getattr(v.ec, "act_var", 1)
+        self.single_observation_space = Box(low=-1.0, high=1.0, shape=obs_one, dtype=np.float32)
+        self.single_action_space = Box(low=-1.0, high=1.0, shape=(n_act,), dtype=np.float32)
+        self.observation_space = Box(low=-1.0, high=1.0, shape=(v.n_envs,) + obs_one, dtype=np.float32)
+        self.action_space = Box(low=-1.0, high=1.0, shape=(v.n_envs, n_act), dtype=np.float32)
         self._needs_reset = True
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -71,13 +83,20 @@ class _VectorBase:
         obs, rew, term, trunc, _ = v.step(actions)
         infos = self._infos()
         final_obs, done_mask = None, None
-        if self.auto_reset:
+        if getattr(v, "device_autoreset", False):
+            # the pool already swapped fresh episodes in on the device: trunc marks them, obs holds their first
+            # observation, v.final_obs the finished episodes' last one.  Nothing is read back here.
+            if self.auto_reset:
+                final_obs, done_mask = v.final_obs, trunc
+        elif self.auto_reset:
             done_mask = trunc.cpu().numpy().astype(bool)          # one small D2H per step: who finished?
             if done_mask.any():
                 final_obs = obs.clone()
                 trunc_keep, rew_keep = trunc.clone(), rew.clone()
                 v.reset(mask=done_mask)                            # masked batched spin-up; writes the new obs rows
                 obs, trunc, rew = v.obs, trunc_keep, rew_keep
+            else:
+                done_mask = None
         return obs, rew, term, trunc, infos, final_obs, done_mask
 
     def close(self):
@@ -100,7 +119,8 @@ class GymVectorEnv(_VectorBase):
         obs, rew, term, trunc, infos, final_obs, done = self._step_core(actions)
         if final_obs is not None:
             infos["final_observation"] = self._out(final_obs)
-            infos["_final_observation"] = done
+            infos["_final_observation"] = (done.bool() if self.as_torch else done.cpu().numpy().astype(bool)) \
+                if torch.is_tensor(done) else done
         if self.as_torch:
             return obs, rew, term, trunc.bool(), infos
         return (obs.cpu().numpy(), rew.cpu().numpy().astype(np.float64), term.cpu().numpy(),
@@ -121,7 +141,7 @@ class SB3VecEnv(_VectorBase):
     def step_wait(self):
         obs, rew, term, trunc, infos, final_obs, done = self._step_core(self._pending)
         dones = trunc.cpu().numpy().astype(bool)
-        fo = final_obs.cpu().numpy() if final_obs is not None else None
+        fo = final_obs.cpu().numpy() if (final_obs is not None and dones.any()) else None
         keys = [k for k, val in infos.items() if not np.isscalar(val)]
         host = {k: (infos[k].cpu().numpy() if torch.is_tensor(infos[k]) else np.asarray(infos[k])) for k in keys}
         info_list = []
@@ -218,7 +238,9 @@ class RecordEpisodeVals:
 def collect_rollout(venv, policy, n_steps, auto_reset=True):
     """PPO-style rollout buffer on the device: ``policy(obs) -> actions`` is called on the env's own tensors, nothing
     leaves the GPU.  Returns ``obs [n, B, ...]``, ``actions [n, B, T]``, ``rewards [n, B]``, ``dones [n, B]`` and the
-    observation after the last step.  Works for the single-agent layout (obs [B, obs_var]) and the multi-agent one
+    observation after the last step.  With a ``DevicePooledVecEnv`` (the rollout loop of a training run) finished
+    episodes are replaced on the device and the loop never synchronises; with a plain ``VecWindFarmEnv`` and
+    ``auto_reset`` they take the masked in-step reset.  Works for the single-agent layout (obs [B, obs_var]) and the multi-agent one
     (``multi_agent=True``: obs [B, T, obs_var], one action per agent -- BASELINE.json cfg 5: obs f32[128, 2048, 8, 2],
     actions f32[128, 2048, 8, 1] after ``unsqueeze(-1)``)."""
     B, T, dev = venv.n_envs, venv.n_turb, venv.device
@@ -227,13 +249,14 @@ def collect_rollout(venv, policy, n_steps, auto_reset=True):
     buf_act = torch.empty((n_steps, B, T), dtype=torch.float32, device=dev)
     buf_rew = torch.empty((n_steps, B), dtype=torch.float32, device=dev)
     buf_done = torch.empty((n_steps, B), dtype=torch.bool, device=dev)
+    pooled = getattr(venv, "device_autoreset", False)     # DevicePooledVecEnv: episodes are replaced on the device
     for i in range(n_steps):
         buf_obs[i] = obs
         act = policy(obs).reshape(B, T).to(torch.float32)
         buf_act[i] = act
         obs, rew, term, trunc, _ = venv.step(act)
         buf_rew[i], buf_done[i] = rew, trunc.bool()
-        if auto_reset:
+        if auto_reset and not pooled:
             done = trunc.cpu().numpy().astype(bool)
             if done.any():
                 venv.reset(mask=done)
