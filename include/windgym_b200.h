@@ -174,7 +174,8 @@ int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* d
  * that order from np_random, Wind_Farm_Env.py:557-568,:715), runs WindFarmEnv.reset's spin-up + measurement fill on
  * them (:722-766) and marks them READY.  mask_row in [0, 8): one per refill in flight (a row may be reused once the
  * stream that carried its previous refill has drained it, e.g. row = stream index).  wg_pool_stats (synchronises):
- * out[0] swaps, out[1] finished episodes deferred for lack of a ready spare (summed over steps), out[2] refills. */
+ * out[0] swaps, out[1] finished episodes deferred for lack of a ready spare (summed over steps), out[2] refills,
+ * out[3] spares waiting for a refill at the latest swap. */
 typedef struct {
   double ws_min, ws_max, ti_min, ti_max, wd_min, wd_max; /* wind: ws_min ... (YAML "wind" section)              */
   double yaw_start;        /* yaw_init "Random": uniform(-yaw_start, yaw_start) (:715)                          */
@@ -190,6 +191,10 @@ int wg_pool_refill(wg_handle* h, void* state, const wg_pool_draw* draw, float* o
 int wg_pool_swap(wg_handle* h, void* state, const uint8_t* truncated, float* obs, uint8_t* swapped, float* final_obs,
                  void* cuda_stream);
 int wg_pool_stats(wg_handle* h, void* state, uint64_t out[8], void* cuda_stream);
+/* Spares waiting for a refill as of the latest wg_pool_swap the device has finished (a word in mapped host memory the
+ * swap kernel publishes; reading it does not synchronise; -1: not available).  The caller uses it to issue
+ * wg_pool_refill when enough spares have been consumed instead of on a fixed step count. */
+int wg_pool_need(wg_handle* h, int32_t* out);
 
 /* TurbulenceFieldSite over a MannTurbulenceField (_def_site, Wind_Farm_Env.py:598-678): attach one periodic
  * turbulence box, shared read-only by every env of the handle, in the two layouts the flow kernel samples:

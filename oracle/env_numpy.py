@@ -214,8 +214,10 @@ class WindFarmEnvOracle:
                  Baseline_comp=False, yaw_init=None, seed=None, dt_sim=1, dt_env=1, yaw_step=1, fill_window=True,
                  eval_mode=False, reset_init=True, noise_seed=0, turb_field=None, added_field=None,
                  induction_control=False, derate_min=0.5):
-        if turbtype not in ("None", "MannFixed", "MannGenerate", "MannLoad"):
-            raise NotImplementedError("turbtype 'Random' (white-noise field) is not restated")
+        if turbtype not in ("None", "MannFixed", "MannGenerate", "MannLoad", "Random"):
+            raise ValueError("Invalid turbulence type specified")   # Wind_Farm_Env.py:666-668
+        # "Random" (RandomTurbulence(ti, ws, seed), :640-644) runs through the same box interface: turb_field is then a
+        # box of independent N(0, 1) cells (the white-noise field frozen on a grid)
         self.turbtype = turbtype
         self.act_var = 2 if induction_control else 1   # extension: [yaw actions | induction actions]
         self.derate_min = derate_min

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -m gpu -q -x > gpurun_out/r05g_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/r05g_pytest.log; tail -30 gpurun_out/r05g_pytest.log
+cat > /tmp/spec.txt <<'EOS'
+cfg3_512 | - | --envs 512 --steps 200 --warmup 10 --no-cpu --no-extras
+cfg2 | - | --steps 100 --warmup 10 --no-cpu --no-extras --no-autoreset
+EOS
+bash scripts/gpu_multi.sh r05g /tmp/spec.txt 0

@@ -271,7 +271,40 @@ def test_device_pool_autoreset_without_the_host(built_lib, multi):
         prev_obs = obs.clone()
     pool.check_flags()
     st = pool.stats
-    assert checked == 3 and st["swapped"] == n_swapped >= 10 and st["refilled"] >= st["swapped"] and st["refill_calls"] >= 30
+    assert checked == 3 and st["swapped"] == n_swapped >= 10 and st["refilled"] >= st["swapped"] and st["refill_calls"] >= 5
     status = pool.inner.state["pool_status"].cpu().numpy()
     assert (status[:B] == 0).all() and set(status[B:].tolist()) <= {1, 2, 3, 4}
     env.close()
+
+
+def test_two_gpus_driven_by_one_process(built_lib):
+    """One process, one handle per GPU.  The opt-in to > 48 KB of dynamic shared memory is a
+    per-DEVICE function attribute: the 64-turbine-capacity flow kernel variant (T > 16) and a finish kernel with long
+    histories need it on every device they run on.  Same inputs -> the same bits on both GPUs."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run through `gpurun --gpus 2`)")
+    cfg = small_config(5, 4, reward="Power_avg", action="wind",
+                       **{"ws_mes.ws_history_length": 400, "ws_mes.ws_window_length": 400})   # 20 turbines, 33 KB of rings
+    B, T = 8, 20
+    rng = np.random.default_rng(2)
+    ws, ti, wd = rng.uniform(9, 13, B), rng.uniform(0.04, 0.1, B), rng.uniform(262, 278, B)
+    yaw0 = rng.uniform(-10, 10, (B, T))
+    acts = rng.uniform(-1, 1, (4, B, T)).astype(np.float32)
+    outs = []
+    envs = [VecWindFarmEnv(V80(), B, config=cfg, device=f"cuda:{i}", fill_window=3) for i in (0, 1)]
+    for env in envs:
+        with torch.cuda.device(env.device):
+            env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+    for a in acts:                                   # interleaved stepping of the two devices
+        for env in envs:
+            with torch.cuda.device(env.device):
+                env.step(torch.as_tensor(a))
+    for env in envs:
+        with torch.cuda.device(env.device):
+            env.check_flags()
+            outs.append((env.obs.cpu().numpy().copy(), env.state["power"].cpu().numpy().copy()))
+            env.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.isfinite(outs[0][0]).all() and outs[0][1].max() > 1e5

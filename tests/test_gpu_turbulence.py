@@ -153,3 +153,48 @@ def test_brick_layout_is_bit_identical_to_the_compact_box(built_lib, monkeypatch
     bricks = run()
     for (o1, p1, s1), (o2, p2, s2) in zip(compact, bricks):
         assert np.array_equal(o1, o2) and np.array_equal(p1, p2) and np.array_equal(s1, s2)
+
+
+def test_turbtype_random_white_noise_box_vs_oracle(built_lib):
+    """turbtype "Random" (Wind_Farm_Env.py:640-644: RandomTurbulence(ti, ws, seed) + the non-synchronised isotropic
+    added-turbulence model): a box of independent N(0, 1) cells through the same sampling path; against the oracle on
+    the same box.  The fluctuations reach the rotors, the wakes barely meander (white noise has no large scales)."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    from windgym_b200.mann import MannBox
+    Nw, Dw = (128, 32, 16), (8.0, 8.0, 8.0)
+    box = MannBox.white_noise(Nxyz=Nw, dxyz=Dw, seed=3, device="cuda:0")
+    ref_box = box.raw[..., :3].permute(3, 0, 1, 2).cpu().numpy().astype(np.float64)
+    assert abs(box.std_u - 1.0) < 0.01
+    lp_std = float(box.lp.std())
+    assert lp_std < 0.2                                      # the low-pass (meandering) part of white noise is small
+    cfg = small_config(2, 2, reward="Power_avg", action="wind")
+    B, T, steps = 2, 4, 6
+    rng = np.random.default_rng(8)
+    ws, ti, wd = rng.uniform(8, 12, B), rng.uniform(0.05, 0.10, B), rng.uniform(264, 276, B)
+    yaw0 = rng.uniform(-10, 10, (B, T))
+    off = rng.uniform(0, 1, (B, 3)) * (np.array(Nw) * np.array(Dw))
+    acts = rng.uniform(-1, 1, (steps, B, T)).astype(np.float32)
+    env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", turbtype="Random", turb_box=box, added_turbulence=False)
+    env.reset(wind=(ws, ti, wd), yaw0=yaw0, turb_offset=off)
+    pw, uvw = [], []
+    for a in acts:
+        o, r, _, _, info = env.step(torch.as_tensor(a))
+        pw.append(info["Power pr turbine agent"].cpu().numpy().copy())
+        uvw.append(torch.stack([env.state[k][:, 0] for k in ("u", "v", "w")], -1).cpu().numpy().copy())
+    env.check_flags(); env.close()
+    pw, uvw = np.array(pw), np.array(uvw)
+    assert np.abs(uvw[..., 2]).max() > 1e-3                   # w' reaches the rotors
+    for b in range(B):
+        field = mn.MannTurbulenceField(ref_box, Dw, lowpass_width=160.0)
+        ref = oracle_rollout(cfg, ws[b:b + 1], ti[b:b + 1], wd[b:b + 1], yaw0[b:b + 1], acts[:, b:b + 1],
+                             turbtype="Random", turb_field=field, reset_kw=dict(turb_offset=off[b]))
+        rel = np.abs(pw[:, b] - ref["power"][0]) / np.maximum(ref["power"][0], 1.0)
+        assert rel.max() < 1e-4, f"env {b}: power rel err {rel.max():.3e}"
+    # the facade builds its own white-noise box for turbtype="Random" and consumes the TF_seed draw (:642)
+    from windgym_b200 import WindFarmEnv
+    fac = WindFarmEnv(V80(), config=small_config(2, 1, reward="Power_avg", action="yaw"), turbtype="Random", seed=4)
+    fac.reset(seed=4)
+    p = [fac.step(np.zeros(2, dtype=np.float32))[4]["Power agent"] for _ in range(10)]
+    assert np.isfinite(p).all() and np.std(p) > 0
+    fac.close()

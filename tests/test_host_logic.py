@@ -70,13 +70,16 @@ def test_config_defaults_and_derived():
     ({"Track_power": True}, {}, NotImplementedError, "Track_power"),                                   # :168
     ({"BaseController": "PyWake"}, {}, ValueError, "BaseController must be either Local or Global"),  # :314
     ({}, dict(fill_window=-3), ValueError, "fill_window must be True or a non-negative integer"),     # :240
-    ({}, dict(turbtype="Random"), NotImplementedError, "turbtype"),
     ({}, dict(turbtype="Mann"), ValueError, "Invalid turbulence type"),                                # :666-668
 ])
 def test_config_errors_match_reference(patch, kw, exc, msg):
     cfg = small_config(2, 2, reward="Baseline", **patch)
     with pytest.raises(exc, match=msg):
         EnvConfig(cfg, V80(), **kw)
+
+
+def test_turbtype_random_is_accepted():
+    assert EnvConfig(small_config(2, 2, reward="Baseline"), V80(), turbtype="Random").turbtype == "Random"   # :640-644
 
 
 def test_reset_integers_match_reference_golden():

@@ -80,6 +80,7 @@ SYMBOLS = {
     "wg_pool_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_pool_refill": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PoolDraw), C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_pool_swap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wg_pool_need": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32)]),
     "wg_pool_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]),
     "wg_set_turbulence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_float, C.c_float]),

@@ -69,10 +69,7 @@ class EnvConfig:
         self.act_var = 2 if self.induction_control else 1
         if not (0.0 < self.derate_min <= 1.0):
             raise ValueError("derate_min must be in (0, 1]")
-        if self.turbtype == "Random":
-            raise NotImplementedError("turbtype='Random' (white-noise RandomTurbulence field) is not built; use a Mann "
-                                      "box type or 'None'")
-        if self.turbtype not in ("None", "MannLoad", "MannGenerate", "MannFixed"):
+        if self.turbtype not in ("None", "MannLoad", "MannGenerate", "MannFixed", "Random"):
             raise ValueError("Invalid turbulence type specified")  # Wind_Farm_Env.py:666-668
         self.yaw_start = 15.0
         self.d_particle = 0.2

@@ -83,7 +83,12 @@ struct wg_handle {
   // L2 residency of the turbulence box: streams that already carry the access-policy window
   std::vector<cudaStream_t> policy_streams;
   size_t tb_lp_bytes = 0;
-  float4* d_lp8 = nullptr;            // library-owned brick copy of the low-pass box (large boxes only)
+  std::vector<size_t> pool_off;       // ... and of the pool view (bind_pool)
+  int* need_host = nullptr;           // mapped host word: spares waiting for a refill (wg_pool_need)
+  int* need_dev = nullptr;            // its device alias
+  std::vector<size_t> state_off;      // offsets of the device view's state pointers (WG_STATE_MEMBERS order)
+  float4* d_lp8 = nullptr;            // library-owned brick copies of the low-pass box and of the raw box
+  float4* d_raw8 = nullptr;
   bool use_bricks = true;             // WG_NO_BRICKS=1: always gather from the caller's lp layout
   bool force_bricks = false;          // WG_FORCE_BRICKS=1: bricks whatever the box size (tests)
 };
@@ -137,54 +142,36 @@ void pin_turbulence_in_l2(wg_handle* h, cudaStream_t s) {
   cudaGetLastError();
 }
 
+// State pointers of the device view: (member, type, field name).  The field offsets are looked up by name once per
+// handle (wg_create); binding a state tensor per call is then plain pointer arithmetic -- this sits on the per-step
+// host path of wg_step / wg_step_host.
+#define WG_STATE_MEMBERS(X)                                                                                              \
+  X(prof, float, "prof") X(pmut, float, "pmut") X(pcon, float, "pcon") X(head, int, "head") X(count, int, "count")      \
+  X(retire, int, "retire") X(n_step, int, "n_step") X(load, int, "load") X(order, int, "order")                         \
+  X(part_acc, int, "part_acc") X(part_keep, int, "part_keep") X(part_arrive, int, "part_arrive") X(work, int2, "work")  \
+  X(yaw, float, "yaw") X(u, float, "u") X(v, float, "v") X(w, float, "w") X(power, float, "power") X(ct, float, "ct")   \
+  X(derate, float, "derate") X(ws, float, "ws") X(ti, float, "ti") X(wd, float, "wd") X(rated, float, "rated_power")    \
+  X(xmax, float, "xmax") X(knu1, float, "knu1") X(k_emit, int, "k_emit") X(time_max, int, "time_max")                   \
+  X(timestep, int, "timestep") X(flags, int, "flags") X(n_push, int, "n_push") X(n_fp, int, "n_fp") X(n_bp, int, "n_bp") \
+  X(spin, int, "spin") X(xr, float, "xr") X(yr, float, "yr") X(xs_sorted, float, "xs_sorted")                           \
+  X(ord_sorted, int, "ord_sorted") X(meas, float, "meas") X(base_pow_mean, float, "base_pow_mean")                      \
+  X(old_yaw, float, "old_yaw") X(rings, float, "rings") X(tb_off, float, "tb_off") X(tb_scale, float, "tb_scale")       \
+  X(fp_ring, float, "farm_pow_ring") X(bp_ring, float, "base_pow_ring")
+
+void resolve_state_offsets(wg_handle* h) {
+  h->state_off.clear();
+#define X(member, type, name) h->state_off.push_back(find_field(h, name)->offset);
+  WG_STATE_MEMBERS(X)
+#undef X
+}
+
 wg::Dev bind(const wg_handle* h, void* state) {
   wg::Dev d = h->dev;
-  d.prof = at<float>(state, h, "prof");
-  d.pmut = at<float>(state, h, "pmut");
-  d.pcon = at<float>(state, h, "pcon");
-  d.head = at<int>(state, h, "head");
-  d.count = at<int>(state, h, "count");
-  d.retire = at<int>(state, h, "retire");
-  d.n_step = at<int>(state, h, "n_step");
-  d.load = at<int>(state, h, "load");
-  d.order = at<int>(state, h, "order");
-  d.part_acc = at<int>(state, h, "part_acc");
-  d.part_keep = at<int>(state, h, "part_keep");
-  d.part_arrive = at<int>(state, h, "part_arrive");
-  d.work = at<int2>(state, h, "work");
-  d.yaw = at<float>(state, h, "yaw");
-  d.u = at<float>(state, h, "u");
-  d.v = at<float>(state, h, "v");
-  d.w = at<float>(state, h, "w");
-  d.power = at<float>(state, h, "power");
-  d.ct = at<float>(state, h, "ct");
-  d.derate = at<float>(state, h, "derate");
-  d.ws = at<float>(state, h, "ws");
-  d.ti = at<float>(state, h, "ti");
-  d.wd = at<float>(state, h, "wd");
-  d.rated = at<float>(state, h, "rated_power");
-  d.xmax = at<float>(state, h, "xmax");
-  d.knu1 = at<float>(state, h, "knu1");
-  d.k_emit = at<int>(state, h, "k_emit");
-  d.time_max = at<int>(state, h, "time_max");
-  d.timestep = at<int>(state, h, "timestep");
-  d.flags = at<int>(state, h, "flags");
-  d.n_push = at<int>(state, h, "n_push");
-  d.n_fp = at<int>(state, h, "n_fp");
-  d.n_bp = at<int>(state, h, "n_bp");
-  d.spin = at<int>(state, h, "spin");
-  d.xr = at<float>(state, h, "xr");
-  d.yr = at<float>(state, h, "yr");
-  d.xs_sorted = at<float>(state, h, "xs_sorted");
-  d.ord_sorted = at<int>(state, h, "ord_sorted");
-  d.meas = at<float>(state, h, "meas");
-  d.base_pow_mean = at<float>(state, h, "base_pow_mean");
-  d.old_yaw = at<float>(state, h, "old_yaw");
-  d.rings = at<float>(state, h, "rings");
-  d.tb_off = at<float>(state, h, "tb_off");
-  d.tb_scale = at<float>(state, h, "tb_scale");
-  d.fp_ring = at<float>(state, h, "farm_pow_ring");
-  d.bp_ring = at<float>(state, h, "base_pow_ring");
+  unsigned char* base = reinterpret_cast<unsigned char*>(state);
+  const size_t* off = h->state_off.data();
+#define X(member, type, name) d.member = reinterpret_cast<type*>(base + *off++);
+  WG_STATE_MEMBERS(X)
+#undef X
   return d;
 }
 
@@ -330,9 +317,11 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
     for (int t = 0; t < T; ++t) { ring_off.push_back(off); ring_chan.push_back(c); off += ch[c]->history_length; }
   const int fch[3] = {0, 1, 3};
   for (int k = 0; k < 3; ++k) { ring_off.push_back(off); ring_chan.push_back(fch[k]); off += ch[fch[k]]->history_length; }
+  off = (off + 3) / 4 * 4;  // rows of the ring block 16-byte aligned: the finish kernel stages them with 16-byte copies
   std::vector<wg::ObsDesc> desc;
   int obs_dim = 0, obs_rows = 1;
   build_desc(*cfg, desc, obs_dim, obs_rows);
+  for (auto& od : desc) od.off = od.kind == 3 ? 0 : ring_off[od.ring];
   if ((e = upload(&h->d_ring_off, ring_off.data(), ring_off.size())) != cudaSuccess ||
       (e = upload(&h->d_ring_chan, ring_chan.data(), ring_chan.size())) != cudaSuccess ||
       (e = upload(&h->d_desc, desc.data(), desc.size())) != cudaSuccess) {
@@ -374,6 +363,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   d.fin_lean = (!cfg->mes.noise && !ti_obs && cfg->power_reward != 3) ? 1 : 0;
   d.ti_lo = (float)cfg->mes.ti_min; d.ti_span = (float)(cfg->mes.ti_max - cfg->mes.ti_min);
   d.ring_off = h->d_ring_off; d.ring_chan = h->d_ring_chan; d.obs_desc = h->d_desc;
+  for (int c = 0; c < 4; ++c) d.ch_base[c] = ring_off[c * T];
+  for (int k = 0; k < 3; ++k) d.farm_off[k] = ring_off[4 * T + k];
   d.tab_ws = h->d_tab_ws; d.tab_p = h->d_tab_p; d.tab_ct = h->d_tab_ct; d.x_pos = h->d_x; d.y_pos = h->d_y;
   h->hist_max = std::max(std::max(cfg->mes.ws.history_length, cfg->mes.wd.history_length), cfg->mes.yaw.history_length);
 
@@ -447,6 +438,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
     wg_destroy(h);
     return cuda_fail(e, "wg_create upload");
   }
+  resolve_state_offsets(h);
   *out = h;
   return WG_OK;
 }
@@ -458,6 +450,8 @@ void wg_destroy(wg_handle* h) {
   cudaFree(h->d_ring_off); cudaFree(h->d_ring_chan); cudaFree(h->d_desc); cudaFree(h->d_copy);
   cudaFree(h->d_done_count);
   cudaFree(h->d_lp8);
+  cudaFree(h->d_raw8);
+  if (h->need_host) cudaFreeHost(h->need_host);
   if (h->flag_host) cudaFreeHost(h->flag_host);
   delete h;
 }
@@ -751,8 +745,9 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   if (!h) return fail(WG_ERR_INVALID, "wg_set_turbulence: null argument");
   wg::Dev& d = h->dev;
   if (!raw_uvw0 && !lp_vw) {  // back to uniform inflow
-    d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr; d.tb_lp8 = nullptr;
+    d.tb_raw = nullptr; d.tb_lp = nullptr; d.tb2_raw = nullptr; d.tb_lp8 = nullptr; d.tb_raw8 = nullptr;
     cudaFree(h->d_lp8); h->d_lp8 = nullptr;
+    cudaFree(h->d_raw8); h->d_raw8 = nullptr;
     h->slots = 0; h->order_state = nullptr;
     return WG_OK;
   }
@@ -776,7 +771,9 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
   // persisting-L2 window of pin_turbulence_in_l2) 0.677 -> 0.608 ms.  The compact layout is the fallback when the
   // bricks do not fit in memory (and WG_NO_BRICKS=1).
   cudaFree(h->d_lp8);
+  cudaFree(h->d_raw8);
   h->d_lp8 = nullptr; d.tb_lp8 = nullptr;
+  h->d_raw8 = nullptr; d.tb_raw8 = nullptr;
   int devid = 0, max_persist = 0;
   cudaGetDevice(&devid);
   cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, devid);
@@ -789,6 +786,16 @@ int wg_set_turbulence(wg_handle* h, const float* raw_uvw0, const float* lp_vw, i
       d.tb_lp8 = h->d_lp8;
     } else {
       cudaGetLastError();  // not enough memory for the bricks: keep gathering from the compact layout
+    }
+    // ... and the raw box (sampled at every rotor's 16 quadrature points each step) as 128-byte bricks of 8 x (u, v, w, 0)
+    const size_t raw_bytes = (size_t)nx * ny * nz * sizeof(float4);
+    if (cudaMalloc(&h->d_raw8, raw_bytes * 8) == cudaSuccess) {
+      cudaError_t e = wg::launch_raw_bricks(d.tb_raw, h->d_raw8, nx, ny, nz, 0);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+      if (e != cudaSuccess) return cuda_fail(e, "wg_set_turbulence: raw brick layout");
+      d.tb_raw8 = h->d_raw8;
+    } else {
+      cudaGetLastError();
     }
   }
   return WG_OK;
@@ -835,20 +842,26 @@ int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* d
   return WG_OK;
 }
 
-static wg::PoolDev bind_pool(const wg_handle* h, void* state) {
+static wg::PoolDev bind_pool(wg_handle* h, void* state) {
+  if (h->pool_off.empty())
+    for (const char* n : {"pool_status", "pool_gen", "pool_swap", "pool_stats", "pool_masks", "pool_ws", "pool_ti",
+                          "pool_ti_flow", "pool_wd", "pool_rated", "pool_tb_scale", "pool_yaw0", "pool_tb_off",
+                          "pool_k_emit", "pool_t_dev", "pool_time_max"})
+      h->pool_off.push_back(find_field(h, n)->offset);
+  unsigned char* b = reinterpret_cast<unsigned char*>(state);
+  const size_t* o = h->pool_off.data();
   wg::PoolDev p{};
-  p.status = at<int>(state, h, "pool_status");
-  p.gen = at<int>(state, h, "pool_gen");
-  p.swap = at<int>(state, h, "pool_swap");
-  p.stats = at<unsigned long long>(state, h, "pool_stats");
-  p.masks = at<uint8_t>(state, h, "pool_masks");
-  p.ws = at<float>(state, h, "pool_ws"); p.ti = at<float>(state, h, "pool_ti");
-  p.ti_flow = at<float>(state, h, "pool_ti_flow"); p.wd = at<float>(state, h, "pool_wd");
-  p.rated = at<float>(state, h, "pool_rated"); p.tb_scale = at<float>(state, h, "pool_tb_scale");
-  p.yaw0 = at<float>(state, h, "pool_yaw0"); p.tb_off = at<float>(state, h, "pool_tb_off");
-  p.k_emit = at<int>(state, h, "pool_k_emit"); p.t_dev = at<int>(state, h, "pool_t_dev");
-  p.time_max = at<int>(state, h, "pool_time_max");
+  p.status = reinterpret_cast<int*>(b + o[0]); p.gen = reinterpret_cast<int*>(b + o[1]);
+  p.swap = reinterpret_cast<int*>(b + o[2]); p.stats = reinterpret_cast<unsigned long long*>(b + o[3]);
+  p.masks = reinterpret_cast<uint8_t*>(b + o[4]);
+  p.ws = reinterpret_cast<float*>(b + o[5]); p.ti = reinterpret_cast<float*>(b + o[6]);
+  p.ti_flow = reinterpret_cast<float*>(b + o[7]); p.wd = reinterpret_cast<float*>(b + o[8]);
+  p.rated = reinterpret_cast<float*>(b + o[9]); p.tb_scale = reinterpret_cast<float*>(b + o[10]);
+  p.yaw0 = reinterpret_cast<float*>(b + o[11]); p.tb_off = reinterpret_cast<float*>(b + o[12]);
+  p.k_emit = reinterpret_cast<int*>(b + o[13]); p.t_dev = reinterpret_cast<int*>(b + o[14]);
+  p.time_max = reinterpret_cast<int*>(b + o[15]);
   p.n_active = h->n_active; p.B = h->cfg.n_envs;
+  p.need_host = h->need_dev;
   return p;
 }
 
@@ -857,6 +870,11 @@ int wg_pool_init(wg_handle* h, void* state, int32_t n_active, void* cuda_stream)
   if (n_active < 1 || n_active >= h->cfg.n_envs)
     return fail(WG_ERR_INVALID, "wg_pool_init: n_active must leave at least one spare slot (1 <= n_active < n_envs)");
   h->n_active = n_active;
+  if (!h->need_host && cudaHostAlloc(reinterpret_cast<void**>(&h->need_host), 64, cudaHostAllocMapped) == cudaSuccess) {
+    if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->need_dev), h->need_host, 0) != cudaSuccess) h->need_dev = nullptr;
+  }
+  cudaGetLastError();
+  if (h->need_host) *h->need_host = h->cfg.n_envs - n_active;
   wg::PoolDev p = bind_pool(h, state);
   std::vector<int> st((size_t)p.B, wg::POOL_ACTIVE);
   for (int b = n_active; b < p.B; ++b) st[b] = wg::POOL_NEED;
@@ -907,6 +925,12 @@ int wg_pool_swap(wg_handle* h, void* state, const uint8_t* truncated, float* obs
   WG_LAUNCH(wg::launch_pool_copy(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, p, obs, final_obs,
                                  h->dev.obs_rows * h->dev.obs_dim, s),
             "wg_pool_copy_kernel");
+  return WG_OK;
+}
+
+int wg_pool_need(wg_handle* h, int32_t* out) {
+  if (!h || !out) return fail(WG_ERR_INVALID, "wg_pool_need: null argument");
+  *out = h->need_host ? *reinterpret_cast<volatile int*>(h->need_host) : -1;
   return WG_OK;
 }
 

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   float* g_rings = d.rings + (size_t)b * d.ring_floats;
   float* g_fp = d.fp_ring + (size_t)b * d.power_avg;
   float* g_bp = d.bp_ring + (size_t)b * d.power_avg;
-  const int per_env = d.ring_floats + 2 * d.power_avg;
+  const int per_env = (d.ring_floats + 2 * d.power_avg + 3) & ~3;  // shared-memory stride of an env: 16-byte aligned
   float* rings = STAGE ? s_dyn + (size_t)warp * per_env : g_rings;
   float* fp = STAGE ? rings + d.ring_floats : g_fp;
   float* bp = STAGE ? fp + d.power_avg : g_bp;
@@ -170,8 +170,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
         float v = s_val[c][t];
         if (!LEAN && d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, t);
         s_val[c][t] = v;
-        const int r = c * T + t;
-        const int o = d.ring_off[r] + np % d.ch_H[c];
+        const int o = d.ch_base[c] + t * d.ch_H[c] + np % d.ch_H[c];
         rings[o] = v;  // deque.append (MesClass.py:66-68, :580-586)
         if (STAGE) g_rings[o] = v;
       }
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
       auto g = [&](int k) { return (double)s_val[c][k]; };
       const double sum = pairwise_sum(g, 0, T);
       const float v = (float)(lane == 2 ? sum : sum / T);
-      const int o = d.ring_off[4 * T + lane] + np % d.ch_H[c];
+      const int o = d.farm_off[lane] + np % d.ch_H[c];
       rings[o] = v;
       if (STAGE) g_rings[o] = v;
     }
@@ -201,7 +200,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
           const int H = d.ch_H[0], L = min(np, H);
           double acc = 0.0;
           for (int t = 0; t < T; ++t) {
-            const float* rg = rings + d.ring_off[t];
+            const float* rg = rings + d.ch_base[0] + t * d.ch_H[0];
             const int st = (np - L) % H;  // oldest sample of the deque; k < L <= H: one conditional wrap
             auto get = [&](int k) { int i = st + k; if (i >= H) i -= H; return (double)rg[i]; };
             acc += (double)scale_f32(calc_ti(get, L), d.ti_lo, d.ti_span);
@@ -209,7 +208,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
           val = (float)(acc / T);
         } else {
           const int H = ds.H, L = min(np, H);
-          const float* rg = rings + d.ring_off[ds.ring];
+          const float* rg = rings + ds.off;
           const int st = (np - L) % H;
           auto get = [&](int k) { int i = st + k; if (i >= H) i -= H; return (double)rg[i]; };
           float raw;
@@ -270,10 +269,10 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     if (a.reward_h) { a.reward_h[b] = (float)rew; a.truncated_h[b] = tr; }
     d.timestep[b] = ts + 1;
   }
-  if (a.done_flag) {  // host-visible completion: every lane's host stores, then one arrival per env
-    __threadfence_system();
-    __syncwarp();
+  if (a.done_flag) {  // host-visible completion: the warp's host stores, ONE system fence (lane 0: the warp barrier
+    __syncwarp();     // orders the other lanes' stores before it, the fence is cumulative), one arrival per env
     if (lane == 0) {
+      __threadfence_system();
       const unsigned t = atomicAdd(a.done_count, 1u);
       if (t == (unsigned)d.Bg - 1u) {
         *a.done_count = 0u;
@@ -334,7 +333,7 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
 }
 
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
-  const size_t smem = sizeof(float) * WG_FIN_WARPS * ((size_t)d.ring_floats + 2 * (size_t)d.power_avg);
+  const size_t smem = sizeof(float) * WG_FIN_WARPS * (((size_t)d.ring_floats + 2 * (size_t)d.power_avg + 3) & ~(size_t)3);
   const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
   if (smem <= 100 * 1024) {
     static size_t configured_dev[WG_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
@@ -648,17 +647,19 @@ __global__ void __launch_bounds__(1024) wg_pool_swap_kernel(const Dev d, const P
   __shared__ int s_src[WG_POOL_MAX_SWAP], s_dst[WG_POOL_MAX_SWAP];
   const int tid = threadIdx.x;
   // ordered compaction (block scan, not atomics): the k-th ready spare goes to the k-th finished env, run after run
-  int nsrc = 0, ndst = 0;
+  int nsrc = 0, ndst = 0, nneed = 0;
   for (int base = p.n_active; base < p.B; base += 1024) {
     const int b = base + tid;
-    int flag = 0;
+    int flag = 0, need = 0;
     if (b < p.B) {
       int st = p.status[b];
       if (st == POOL_PENDING) { p.status[b] = POOL_NEED; st = POOL_NEED; }
       flag = st == POOL_READY;
+      need = st == POOL_NEED;
     }
     scan[tid] = flag;
     const int total = __syncthreads_count(flag);
+    nneed += __syncthreads_count(need);
     plan_exclusive_scan(scan, wsum);
     if (flag && nsrc + scan[tid] < WG_POOL_MAX_SWAP) s_src[nsrc + scan[tid]] = b;
     nsrc += total;
@@ -687,19 +688,21 @@ __global__ void __launch_bounds__(1024) wg_pool_swap_kernel(const Dev d, const P
     p.swap[2 * WG_POOL_MAX_SWAP] = n;
     if (n) atomicAdd(&p.stats[0], (unsigned long long)n);
     if (ndst > n) atomicAdd(&p.stats[1], (unsigned long long)(ndst - n));
+    p.stats[3] = (unsigned long long)nneed;
+    if (p.need_host) *p.need_host = nneed;
   }
 }
 
-// Copy the paired spares over the finished envs: grid (chunks, WG_POOL_MAX_SWAP); pair k >= n: nothing to do.
+// Copy the paired spares over the finished envs: grid (chunks, 8 pair lanes); no pairs: nothing to do.
 // The finished env's last observation is kept in final_obs (the "terminal observation" of the vector-env APIs), its
 // observation row then becomes the spare's reset observation.
 __global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __restrict__ state, const CopyField* __restrict__ fields,
                                                            int n_fields, const PoolDev p, float* __restrict__ obs,
                                                            float* __restrict__ final_obs, int obs_floats) {
-  const int k = blockIdx.y;
-  if (k >= p.swap[2 * WG_POOL_MAX_SWAP]) return;
-  const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
+  const int n = p.swap[2 * WG_POOL_MAX_SWAP];
   const unsigned nchunk = gridDim.x, chunk = blockIdx.x;
+  for (int k = blockIdx.y; k < n; k += gridDim.y) {
+  const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
   for (int fi = 0; fi < n_fields; ++fi) {
     const CopyField f = fields[fi];
     const size_t so = (size_t)src * f.per_env, dof = (size_t)dst * f.per_env;
@@ -721,6 +724,7 @@ __global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __rest
       if (final_obs) final_obs[(size_t)dst * obs_floats + i] = obs[(size_t)dst * obs_floats + i];
       obs[(size_t)dst * obs_floats + i] = obs[(size_t)src * obs_floats + i];
     }
+  }
 }
 
 cudaError_t launch_pool_claim(const Dev& d, const PoolDev& p, const PoolDraw& w, int mask_row, cudaStream_t s) {
@@ -737,7 +741,7 @@ cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* trun
 }
 cudaError_t launch_pool_copy(unsigned char* state, const CopyField* fields, int n_fields, const PoolDev& p, float* obs,
                              float* final_obs, int obs_floats, cudaStream_t s) {
-  wg_pool_copy_kernel<<<dim3(32, WG_POOL_MAX_SWAP), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
+  wg_pool_copy_kernel<<<dim3(32, 8), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
   return cudaGetLastError();
 }
 

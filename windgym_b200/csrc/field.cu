@@ -98,6 +98,24 @@ __global__ void __launch_bounds__(256) wg_brick_kernel(const float2* __restrict_
   }
 }
 
+// 128-byte bricks of the raw box: cell (i, j, k) <- its 8 periodic corners (u, v, w, 0), in gather4's loop order
+__global__ void __launch_bounds__(256) wg_raw_brick_kernel(const float4* __restrict__ raw, float4* __restrict__ raw8, int nx,
+                                                           int ny, int nz) {
+  const size_t n = (size_t)nx * ny * nz * 8;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = e >> 3;
+    const int corner = (int)(e & 7), a = corner >> 2, b = (corner >> 1) & 1, cc = corner & 1;
+    const int k = (int)(c % nz), j = (int)((c / nz) % ny), i = (int)(c / ((size_t)nz * ny));
+    const int ii = a ? (i + 1 == nx ? 0 : i + 1) : i, jj = b ? (j + 1 == ny ? 0 : j + 1) : j, kk = cc ? (k + 1 == nz ? 0 : k + 1) : k;
+    raw8[e] = raw[((size_t)ii * ny + jj) * nz + kk];
+  }
+}
+
+cudaError_t launch_raw_bricks(const float4* raw, float4* raw8, int nx, int ny, int nz, cudaStream_t s) {
+  wg_raw_brick_kernel<<<148 * 16, 256, 0, s>>>(raw, raw8, nx, ny, nz);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_bricks(const float2* lp, float4* lp8, int nx, int ny, int nz, cudaStream_t s) {
   wg_brick_kernel<<<148 * 16, 256, 0, s>>>(lp, lp8, nx, ny, nz);
   return cudaGetLastError();

@@ -847,6 +847,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
         count_below2(sh.xs, xs_top, xn, xe, cn, ce);
       };
       if (!TURB) move_and_search();
+      if (TURB && Lc.valid) prefetch_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo);
       WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches, moves, plane searches
       mbar_wait(bar, phase);
       phase ^= 1u;

@@ -42,6 +42,7 @@ struct ObsDesc {
   float lo, span; // scaling: 2*(v-lo)/span-1, span = float32(double(hi)-double(lo))
   int32_t H, N, W; // history_length / history_N / window_length of the channel (copied here: no dynamic indexing
                    // of the kernel-parameter arrays in the observation loop)
+  int32_t off;     // offset of the ring inside the env's ring block (kind 0, 1, 2)
 };
 
 struct Dev {
@@ -64,6 +65,8 @@ struct Dev {
   float noise_std[4];
   unsigned long long noise_seed;
   float ti_lo, ti_span;
+  int ch_base[4];         // offset of channel c's first turbine ring (ring of turbine t: ch_base[c] + t ch_H[c])
+  int farm_off[3];        // offsets of the farm-level rings ws, wd, power
   const int* ring_off;    // [n_rings]
   const int* ring_chan;   // [n_rings]
   const ObsDesc* obs_desc;  // [obs_rows * obs_dim]
@@ -103,7 +106,9 @@ struct Dev {
   const float2* tb_lp;    // [Nx,Ny,Nz] (v, w) low-pass filtered in y, z: moves the wake centres
   const float4* tb_lp8;   // [Nx,Ny,Nz][4] the same field as 64-byte BRICKS: cell (i,j,k) holds its 8 trilinear corners
                           // (i+a, j+b, k+c), periodic -- one aligned 64-byte read per sample instead of 8 scattered
-                          // sectors; built by the library for boxes too large to stay in L2 (null: gather from tb_lp)
+                          // sectors; built by the library at wg_set_turbulence (null: gather from tb_lp)
+  const float4* tb_raw8;  // [Nx,Ny,Nz][8] the raw box as 128-byte bricks (8 corners x (u, v, w, 0)): one line per rotor-point
+                          // sample; null: gather from tb_raw
   int tb_n[3];
   float tb_inv_d[3], tb_inv_n[3], tb_len_x;
   float *tb_off;          // [B,3] position of the env inside the box [m]
@@ -162,6 +167,8 @@ struct PoolDev {
   int* swap;            // [2 * WG_POOL_MAX_SWAP + 1]  src[], dst[], n of the current step
   unsigned long long* stats;  // [8] swapped, deferred (finished episodes that found no ready spare), refilled
   uint8_t* masks;       // [WG_POOL_MASKS, B]
+  volatile int* need_host;  // mapped host word: spares waiting for a refill, published by every swap (host polls it
+                            // without synchronising to decide when a refill is worth its ~60 launches); may be null
   // reset arguments of the slots being refilled (the arrays wg_reset takes, drawn on the device)
   float *ws, *ti, *ti_flow, *wd, *yaw0, *rated, *tb_off, *tb_scale;
   int *k_emit, *t_dev, *time_max;
@@ -263,9 +270,35 @@ __device__ __forceinline__ float2 sample_lp(const Dev& d, float x, float y, floa
     }
   return make_float2(v * scale, w * scale);
 }
+// pull the brick a wake-centre sample will read towards L2 (issued as soon as the station's position is known, consumed
+// after the tile wait: the DRAM latency of the random read hides behind the tile's flight)
+__device__ __forceinline__ void prefetch_lp(const Dev& d, float x, float y, float z, float xs, float yo, float zo) {
+  if (!d.tb_lp8) return;
+  const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(d.tb_lp8 + (((size_t)b.i[0] * d.tb_n[1] + b.j[0]) * d.tb_n[2] + b.k[0]) * 4));
+}
 __device__ __forceinline__ float4 sample_raw(const Dev& d, float x, float y, float z, float xs, float yo, float zo,
                                              float scale) {
   const BoxIdx b = box_index(d, (x - xs) * d.tb_inv_d[0], (y + yo) * d.tb_inv_d[1], (z + zo) * d.tb_inv_d[2]);
+  if (d.tb_raw8) {  // brick of cell (i0, j0, k0): the 8 corners in gather4's loop order, same arithmetic -> same bits
+    const float4* p = d.tb_raw8 + (((size_t)b.i[0] * d.tb_n[1] + b.j[0]) * d.tb_n[2] + b.k[0]) * 8;
+    float u = 0.f, v = 0.f, w = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const float wxy = (a ? b.fx : 1.f - b.fx) * (bb ? b.fy : 1.f - b.fy);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float wt = wxy * (c ? b.fz : 1.f - b.fz);
+          const float4 q = __ldg(p + (a * 4 + bb * 2 + c));
+          u = fmaf(wt, q.x, u);
+          v = fmaf(wt, q.y, v);
+          w = fmaf(wt, q.z, w);
+        }
+      }
+    return make_float4(u * scale, v * scale, w * scale, 0.f);
+  }
   const float4 q = gather4(d.tb_raw, d.tb_n, b);
   return make_float4(q.x * scale, q.y * scale, q.z * scale, 0.f);
 }
@@ -292,6 +325,7 @@ cudaError_t launch_pool_claim(const Dev& d, const PoolDev& p, const PoolDraw& w,
 cudaError_t launch_pool_publish(const PoolDev& p, int mask_row, cudaStream_t s);
 cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* truncated, uint8_t* swapped, cudaStream_t s);
 cudaError_t launch_bricks(const float2* lp, float4* lp8, int nx, int ny, int nz, cudaStream_t s);
+cudaError_t launch_raw_bricks(const float4* raw, float4* raw8, int nx, int ny, int nz, cudaStream_t s);
 int flow_resident_ctas(const Dev& d);
 cudaError_t launch_reset_init(const Dev& d, const ResetDevArgs& a, cudaStream_t s);
 // one state field as the env-copy kernel sees it: n_rep blocks of B envs, per_env bytes each

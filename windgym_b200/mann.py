@@ -129,6 +129,19 @@ class MannBox:
         return cls(uvw, dxyz, lowpass_width=lowpass_width)
 
     @classmethod
+    def white_noise(cls, Nxyz=(1024, 128, 32), dxyz=(8.0, 8.0, 8.0), seed=1, device="cuda:0", lowpass_width=160.0):
+        """``RandomTurbulence(ti, ws, seed)`` of turbtype "Random" (Wind_Farm_Env.py:640-644): uncorrelated Gaussian
+        fluctuations, here as a periodic box of independent N(0, 1) cells per component (``scale_for`` makes
+        std(u) = TI * U).  White noise has no large scales: its low-pass (meandering) part is close to zero by
+        construction.  Between cell centres the trilinear sampling of the flow kernel averages neighbouring cells
+        (variance at a point between 1/8 and 1 of the cell variance) -- a rotor average over 16 points spread over 80 m
+        of 8 m cells is insensitive to that."""
+        dev = torch.device(device)
+        gen = torch.Generator(device=dev).manual_seed(int(seed))
+        uvw = torch.randn((3,) + tuple(int(n) for n in Nxyz), generator=gen, device=dev, dtype=torch.float32)
+        return cls(uvw, dxyz, lowpass_width=lowpass_width)
+
+    @classmethod
     def isotropic_unit(cls, D, seed=1, device="cuda:0", Nxyz=(128, 64, 64), noise=None):
         """Box of the wake-added turbulence (``SynchronizedAutoScalingIsotropicMannTurbulence``): isotropic (Gamma = 0),
         small scales (L = D/8, cells of D/16), normalised to unit standard deviation of u."""

@@ -197,7 +197,7 @@ class DevicePooledVecEnv:
     Same idea as ``PooledVecEnv`` -- ``reserve`` spare env slots behind the ``n_envs`` active ones, spun up in the
     background and copied over envs whose episode ended -- but every per-step decision is made on the device:
     ``wg_pool_swap`` (two launches on the stepping stream) pairs finished episodes with ready spares and copies them,
-    ``wg_pool_refill`` (every ``refill_every`` steps, round robin over background streams) draws new wind conditions
+    ``wg_pool_refill`` (whenever enough spares have been consumed, round robin over background streams) draws new wind conditions
     for the consumed spares with a counter-based generator, runs the masked reset on them and marks them ready.  No
     truncation flags are read back, no host-side bookkeeping per episode.  ``step()`` returns the new episode's first
     observation for the swapped envs and ``truncated`` = the envs that were swapped in this step (an episode that
@@ -211,7 +211,7 @@ class DevicePooledVecEnv:
 
     device_autoreset = True
 
-    def __init__(self, turbine, n_envs, reserve=None, refill_every=8, n_streams=8, **env_kwargs):
+    def __init__(self, turbine, n_envs, reserve=None, refill_every=4, n_streams=8, **env_kwargs):
         import ctypes as C
         from . import _lib
         self._C, self._lib_mod = C, _lib
@@ -220,7 +220,7 @@ class DevicePooledVecEnv:
         # step: the spares in flight are (finished episodes per second) x (spin-up latency) ~ 250-400 for the 4x4 farm
         # at any batch size from 512 envs up; small batches are bounded by 4 spares per env
         self.reserve = int(reserve) if reserve is not None else max(32, min(384, 4 * self.n_envs), self.n_envs // 8)
-        self.refill_every = max(1, int(refill_every))
+        self.refill_every = max(1, int(refill_every))      # steps between attempts to issue a refill (see _refill)
         self.inner = VecWindFarmEnv(turbine, self.n_envs + self.reserve, **env_kwargs)
         v = self.inner
         if v.sample_site is not None:
@@ -234,7 +234,9 @@ class DevicePooledVecEnv:
         self.lib = v.lib
         n_streams = min(max(1, int(n_streams)), 8)          # one refill mask row per stream (WG_POOL_MASKS)
         self._bgs = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self._bg_events = [None] * n_streams
         self._n_refill = 0
+        self._n_tried = 0
         self._steps = 0
         B = self.n_envs
         self.state = {k: (t[:, :B] if k == "pmut" else t[:B]) for k, t in v.state.items()
@@ -354,13 +356,27 @@ class DevicePooledVecEnv:
             self._refill()                                       # all spares: one batched spin-up
         return self.obs, self._info()
 
-    def _refill(self):
-        k = self._n_refill % len(self._bgs)
-        bg = self._bgs[k]
+    def _refill(self, wait=False):
+        """Issue one refill sequence (claim + draw, masked reset, publish: ~60 launches) on a background stream that is
+        idle.  A spin-up takes ~20 ms whatever it holds, so the pace is set by the streams, not by the step count: at
+        most one sequence is queued per stream (its completion event is polled, never waited for), what a sequence
+        claims is decided on the device when it starts.  No idle stream: nothing is issued (the next attempt is a few
+        steps away)."""
         v = self.inner
-        self._lib_mod.check(self.lib.wg_pool_refill(v._h, v._step_ptrs[0], self._C.byref(self._draw_args), v._step_ptrs[1],
-                                                    k, self._C.c_void_p(bg.cuda_stream)))
-        self._n_refill += 1
+        for _ in range(len(self._bgs)):
+            k = self._n_tried % len(self._bgs)
+            self._n_tried += 1
+            ev = self._bg_events[k]
+            if ev is None or ev.query():
+                bg = self._bgs[k]
+                self._lib_mod.check(self.lib.wg_pool_refill(v._h, v._step_ptrs[0], self._C.byref(self._draw_args),
+                                                            v._step_ptrs[1], k, self._C.c_void_p(bg.cuda_stream)))
+                ev = torch.cuda.Event()
+                ev.record(bg)
+                self._bg_events[k] = ev
+                self._n_refill += 1
+                return True
+        return False
 
     def step(self, actions):
         if not self._ready:

@@ -159,6 +159,9 @@ class VecWindFarmEnv:
                 box = MannBox.generate(0.1, 33.6, 3.9, Nxyz=(4096, 512, 64), dxyz=(ec.D / 20, ec.D / 10, ec.D / 10),
                                        seed=0 if self.seed is None else int(self.seed), device=self.device,
                                        lowpass_width=2 * ec.D)
+            elif ec.turbtype == "Random":        # :640-644: RandomTurbulence(ti, ws, seed) -- a white-noise box
+                box = MannBox.white_noise(seed=0 if self.seed is None else int(self.seed), device=self.device,
+                                          lowpass_width=2 * ec.D)
             else:                                 # MannLoad, :612-617: one of the files under TurbBox
                 files = [TurbBox] if os.path.isfile(str(TurbBox)) else sorted(
                     f for ext in ("*.npz", "*.npy", "*.nc") for f in glob.glob(os.path.join(str(TurbBox), ext)))
@@ -230,7 +233,7 @@ class VecWindFarmEnv:
         # against numpy in tests/test_host_logic.py) instead of one Generator object per env (17 us each).
         idx = np.fromiter(envs, dtype=np.int64)
         if (seed is not None and not (B == 1 and self._episode == 0) and self.sample_site is None
-                and ec.turbtype not in ("MannGenerate", "MannLoad") and 0 <= int(seed) < 2 ** 32 and idx.size > 8
+                and ec.turbtype not in ("MannGenerate", "MannLoad", "Random") and 0 <= int(seed) < 2 ** 32 and idx.size > 8
                 and not getattr(self, "_no_fast_rng", False)):
             n_yaw = T if ec.yaw_init_mode == "Random" else 0
             u = uniform_streams(int(seed), idx, self._episode, 3 + n_yaw)
@@ -258,7 +261,7 @@ class VecWindFarmEnv:
                 wd[i] = np.clip(wd_s, ec.wd_min, ec.wd_max)
                 ws[i] = np.clip(ws_s, ec.ws_min, ec.ws_max)
                 ti[i] = rng.uniform(low=ec.TI_min, high=ec.TI_max)
-            if ec.turbtype == "MannGenerate":    # TF_seed draw sits between wd and yaw (Wind_Farm_Env.py:623)
+            if ec.turbtype in ("MannGenerate", "Random"):    # TF_seed draw sits between wd and yaw (:623, :642)
                 self._tf_seed[i] = int(rng.integers(0, 100000))
             elif ec.turbtype == "MannLoad":      # np_random.choice(TF_files) sits there too (:614): keep the stream aligned
                 rng.choice(max(1, len(getattr(self, "_tf_files", ()))))
