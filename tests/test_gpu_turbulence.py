@@ -198,3 +198,39 @@ def test_turbtype_random_white_noise_box_vs_oracle(built_lib):
     p = [fac.step(np.zeros(2, dtype=np.float32))[4]["Power agent"] for _ in range(10)]
     assert np.isfinite(p).all() and np.std(p) > 0
     fac.close()
+
+
+def test_mannload_reads_netcdf4_boxes(built_lib, tmp_path):
+    """turbtype "MannLoad" (Wind_Farm_Env.py:611-618): MannTurbulenceField.from_netcdf on the files under TurbBox --
+    NetCDF-4 / HDF5 files read by the built-in reader (no netCDF4 / h5py in this image); FarmEval.update_tf
+    (FarmEval.py:86-90) switches the file."""
+    import torch
+    from tests import hdf5_writer
+    from windgym_b200 import V80, FarmEval, WindFarmEnv
+    from windgym_b200.mann import MannBox
+    rng = np.random.default_rng(4)
+    shape, d3 = (64, 16, 8), (6.0, 12.0, 12.0)
+    axes = [np.arange(n) * d for n, d in zip(shape, d3)]
+    boxes = []
+    for k in range(2):
+        uvw = rng.normal(size=(3,) + shape).astype(np.float32)
+        p = str(tmp_path / f"TF_{k}.nc")
+        hdf5_writer.write(p, {"uvw": uvw, "x": axes[0], "y": axes[1], "z": axes[2]}, chunked=("uvw",) if k else ())
+        boxes.append((p, uvw))
+    box = MannBox.from_file(boxes[1][0], device="cuda:0")
+    assert box.Nxyz == shape and box.dxyz == d3
+    assert np.array_equal(box.raw[..., :3].permute(3, 0, 1, 2).cpu().numpy(), boxes[1][1])
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    env = WindFarmEnv(V80(), config=cfg, turbtype="MannLoad", TurbBox=str(tmp_path), seed=3, device="cuda:0")
+    assert env.vec.turb_box.Nxyz == shape
+    env.reset(seed=3)
+    p = [env.step(np.zeros(2, dtype=np.float32))[4]["Power agent"] for _ in range(8)]
+    assert np.isfinite(p).all() and np.std(p) > 0
+    env.close()
+    fe = FarmEval(V80(), config=cfg, turbtype="MannLoad", TurbBox=boxes[0][0], yaw_init="Zeros", seed=1, device="cuda:0")
+    fe.update_tf(boxes[1][0])
+    assert np.array_equal(fe.vec.turb_box.raw[..., :3].permute(3, 0, 1, 2).cpu().numpy(), boxes[1][1])
+    fe.set_wind_vals(ws=10, ti=0.08, wd=270)
+    fe.reset()
+    assert np.isfinite(fe.step(np.zeros(2, dtype=np.float32))[1])
+    fe.close()

@@ -147,3 +147,42 @@ def test_fast_rng_replicates_numpy_streams():
     for a, b in zip(*out):
         assert np.array_equal(a, b)
     assert out[0][0][3] != 0 and out[0][0][0] == 0 and np.abs(out[0][3][10]).max() <= 15
+
+
+# ------------------------------------------------------------------------------------------------ NetCDF-4 / HDF5 boxes
+def test_hdf5_min_reads_a_mann_box_file(tmp_path):
+    """windgym_b200/hdf5_min.py on a synthetic HDF5 file in the 'earliest' layout (superblock 0, version-1 headers,
+    symbol-table group) with a contiguous and a chunked + shuffle + deflate copy of the field."""
+    from tests import hdf5_writer
+    from windgym_b200 import hdf5_min
+    rng = np.random.default_rng(0)
+    uvw = rng.normal(size=(3, 12, 6, 5)).astype(np.float32)
+    x, y, z = np.arange(12) * 4.0, np.arange(6) * 8.0, np.arange(5) * 8.0 + 10.0
+    for chunked in ((), ("uvw",)):
+        p = str(tmp_path / f"box_{len(chunked)}.nc")
+        hdf5_writer.write(p, {"uvw": uvw, "x": x, "y": y, "z": z, "seed": np.array([7], dtype=np.int64)}, chunked=chunked)
+        assert hdf5_min.list_datasets(p) == ["seed", "uvw", "x", "y", "z"]
+        got, dxyz = hdf5_min.read_mann_box(p)
+        assert got.dtype == np.float32 and np.array_equal(got, uvw) and dxyz == (4.0, 8.0, 8.0)
+        assert hdf5_min.read_datasets(p, names=("seed",))["seed"].tolist() == [7]
+    with pytest.raises(ValueError):
+        (tmp_path / "junk.nc").write_bytes(b"not hdf5" * 100)
+        hdf5_min.read_mann_box(str(tmp_path / "junk.nc"))
+
+
+@pytest.mark.reference
+def test_hdf5_min_reads_the_reference_netcdf4_file():
+    """The reference's own NetCDF-4 file (xarray -> netCDF4: superblock 2, version-2 object headers, dense links in a
+    fractal heap, contiguous float64 datasets): names, shapes and internal consistency of what the reader returns."""
+    from windgym_b200 import hdf5_min
+    path = "/root/reference/examples/PPO_eval.nc"
+    if not os.path.isfile(path):
+        pytest.skip("reference checkout not present")
+    ds = hdf5_min.read_datasets(path)
+    assert set(ds) >= {"time", "ws", "wd", "TI", "turb", "powerF_a", "powerT_a", "yaw_a", "ws_a", "reward", "pct_inc"}
+    assert ds["ws"].tolist() == [10, 11, 12, 14] and ds["wd"].tolist() == [260, 265, 270, 275, 280]
+    assert ds["time"].shape == (2039,) and np.all(np.diff(ds["time"]) == 1.0)
+    assert ds["powerT_a"].shape == (2039, 4, 4, 5, 1, 1) and ds["powerF_a"].shape == (2039, 4, 5, 1, 1)
+    ok = np.isfinite(ds["powerF_a"])
+    assert ok.mean() > 0.9 and np.array_equal(ds["powerF_a"][ok], ds["powerT_a"].sum(axis=1)[ok])   # farm = sum of turbines
+    assert np.nanmax(ds["powerT_a"]) <= 2.0e6 and np.nanmin(ds["yaw_a"]) >= -45 and np.nanmax(ds["yaw_a"]) <= 45

@@ -70,6 +70,7 @@ struct wg_handle {
   int n_work = 0;                     // entries of the current table
   int tail_units = 0, tail_parts = 1; // WG_TAIL_UNITS / WG_TAIL_PARTS in the environment (A/B measurements)
   bool use_split = true;              // WG_NO_SPLIT=1: never cut a farm into parts
+  bool two_wave = true;               // WG_NO_TWOWAVE=1: between 1 and 2 waves of farms, keep one CTA per farm
   bool use_pdl = true;                // WG_NO_PDL=1: plain stream order between the flow and the finish kernel
   // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
   // number, and the pinned host ranges already identified (host base, device alias, bytes)
@@ -408,7 +409,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "part_acc", 1, {B, F, 5, T});
   add_field(h, "part_keep", 1, {B, F, T});
   add_field(h, "part_arrive", 1, {B, F});
-  h->work_cap = std::max(B * F * 2, 2048);
+  h->work_cap = std::max(B * F * 2, 4096);
   add_field(h, "work", 1, {h->work_cap, 2});
   // device-side spare pool (wg_pool_*): slot status, RNG generation, the step's swap list, counters, refill masks and
   // the reset arguments of the slots being refilled
@@ -425,6 +426,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   h->use_bricks = !(no_br && no_br[0] == '1');
   const char* f_br = getenv("WG_FORCE_BRICKS");
   h->force_bricks = f_br && f_br[0] == '1';
+  const char* no_tw = getenv("WG_NO_TWOWAVE");
+  h->two_wave = !(no_tw && no_tw[0] == '1');
   const char* no_pdl = getenv("WG_NO_PDL");
   h->use_pdl = !(no_pdl && no_pdl[0] == '1');
   const char* no_zc = getenv("WG_NO_ZEROCOPY");
@@ -568,7 +571,9 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
       wg::PlanArgs pa{};
       pa.slots = h->slots;
       if (U < h->slots) {
-        pa.n_work = h->slots;
+        pa.target = pa.n_work = h->slots;
+      } else if (U < 2 * h->slots && h->two_wave) {
+        pa.target = pa.n_work = 2 * h->slots;
       } else {
         pa.tail_units = std::min(h->tail_units, U);
         pa.tail_parts = pa.tail_units > 0 ? h->tail_parts : 1;

@@ -96,14 +96,29 @@ __device__ __noinline__ float calc_ti(Get get, int L) {  // rare observation kin
 // LEAN = true: the common configuration -- no measurement noise, no TI observations, no Power_diff reward -- compiled
 // without those paths (a third of the code: this 20 us single-wave kernel pays for every instruction line it has
 // to fetch cold); the host picks the variant from the handle's configuration.
-template <bool STAGE, bool LEAN>
-__global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const Dev d, const FinishArgs a) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, T = d.T;
+// PAIR = true (batches of at most one wave of envs): TWO warps per env.  The kernel is a serial chain of ~1500
+// dependent warp instructions per env; the measurement chain (ring pushes, observation windows) and the power chain
+// (power deques, reward, truncation) only share their inputs, so they run side by side on the two warps -- same
+// arithmetic, same bits, ~40 % less latency.  The warps of an env meet at a named barrier (id 1 + env slot).
+template <bool PAIR>
+__device__ __forceinline__ void env_barrier(int slot) {
+  if (PAIR) asm volatile("bar.sync %0, 64;" ::"r"(1 + slot) : "memory");
+  else __syncwarp();
+}
+template <bool STAGE, bool LEAN, bool PAIR>
+__global__ void __launch_bounds__(WG_FIN_WARPS * 32 * (PAIR ? 2 : 1), PAIR ? 4 : 8) wg_finish_kernel(const Dev d, const FinishArgs a) {
+  const int warp_cta = threadIdx.x >> 5, T = d.T;
+  const int warp = PAIR ? warp_cta >> 1 : warp_cta;        // env slot of the CTA
+  const int role = PAIR ? warp_cta & 1 : 0;                // PAIR: 0 = measurement chain, 1 = power chain
+  const int lane = threadIdx.x & 31;
+  const int lane_e = PAIR ? (threadIdx.x & 63) : lane, n_e = PAIR ? 64 : 32;   // thread index / threads of the env
+  const bool do_mes = !PAIR || role == 0, do_pow = !PAIR || role == 1;
   const int b = d.b0 + blockIdx.x * WG_FIN_WARPS + warp;
   if (b >= d.b0 + d.Bg) return;
   if (a.mask && !a.mask[b]) return;
   extern __shared__ __align__(16) float s_dyn[];
   __shared__ float s_vals[WG_FIN_WARPS][4][WG_MAX_T];
+  __shared__ float s_noisy[PAIR ? WG_FIN_WARPS : 1][4][PAIR ? WG_MAX_T : 1];
   float (*s_val)[WG_MAX_T] = s_vals[warp];
   float* g_rings = d.rings + (size_t)b * d.ring_floats;
   float* g_fp = d.fp_ring + (size_t)b * d.power_avg;
@@ -115,11 +130,11 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   if (STAGE) {  // asynchronous copies (LDGSTS): every load of the env is in flight before the first wait
     const bool v16 = ((d.ring_floats | per_env) & 3) == 0;  // rows 16-byte aligned in global and shared memory
     if (v16) {
-      for (int i = lane * 4; i < d.ring_floats; i += 128) cp_async16(rings + i, g_rings + i);
+      for (int i = lane_e * 4; i < d.ring_floats; i += 4 * n_e) cp_async16(rings + i, g_rings + i);
     } else {
-      for (int i = lane; i < d.ring_floats; i += 32) cp_async4(rings + i, g_rings + i);
+      for (int i = lane_e; i < d.ring_floats; i += n_e) cp_async4(rings + i, g_rings + i);
     }
-    for (int i = lane; i < d.power_avg; i += 32) { cp_async4(fp + i, g_fp + i); cp_async4(bp + i, g_bp + i); }
+    for (int i = lane_e; i < d.power_avg; i += n_e) { cp_async4(fp + i, g_fp + i); cp_async4(bp + i, g_bp + i); }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
   // scalars of the env, loaded up front (used by the pushes and the reward at the end)
@@ -133,16 +148,16 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
   const float g_base_pow = d.base_pow_mean[b];
   if (a.flags & (FIN_PUSH_MES | FIN_PUSH_FP))
-    for (int t = lane; t < T; t += 32) {
+    for (int t = lane_e; t < T; t += n_e) {
       const float* src[4] = {a.in_ws, a.in_wd, a.in_yaw, a.in_power};
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         s_val[c][t] = (a.flags & FIN_MEAS_FROM_ARGS) ? src[c][b * T + t] : d.meas[(b * 4 + c) * T + t];
     }
   if (STAGE) asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncwarp();
+  env_barrier<PAIR>(warp);
 
-  if (a.flags & FIN_PUSH_FP) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977): noise-free means
+  if (do_pow && (a.flags & FIN_PUSH_FP)) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977): noise-free means
     if (lane == 0) {
       auto gp = [&](int k) { return (double)s_val[3][k]; };
       const float v = (float)pairwise_sum(gp, 0, T);
@@ -152,7 +167,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     }
     nfp_tot += 1;
   }
-  if (a.flags & FIN_PUSH_BP) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
+  if (do_pow && (a.flags & FIN_PUSH_BP)) {  // base_pow_deq.append(mean(baseline farm sums)) (:978-979)
     if (lane == 0) {
       const float v = g_base_pow;
       bp[nbp_tot % d.power_avg] = v;
@@ -161,15 +176,17 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     }
     nbp_tot += 1;
   }
-  __syncwarp();  // s_val is overwritten with the noisy values below
+  __syncwarp();  // one warp per env: s_val is overwritten with the noisy values below
+  float (*s_push)[WG_MAX_T] = s_val;   // PAIR: the measurement warp keeps its noisy copy apart from the power warp's input
+  if (PAIR) s_push = reinterpret_cast<float (*)[WG_MAX_T]>(&s_noisy[warp][0][0]);
 
-  if (a.flags & FIN_PUSH_MES) {
+  if (do_mes && (a.flags & FIN_PUSH_MES)) {
     for (int t = lane; t < T; t += 32) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float v = s_val[c][t];
         if (!LEAN && d.noise && d.noise_std[c] > 0.f) v += d.noise_std[c] * normal_noise(d.noise_seed, b, np, c, t);
-        s_val[c][t] = v;
+        s_push[c][t] = v;
         const int o = d.ch_base[c] + t * d.ch_H[c] + np % d.ch_H[c];
         rings[o] = v;  // deque.append (MesClass.py:66-68, :580-586)
         if (STAGE) g_rings[o] = v;
@@ -178,7 +195,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     __syncwarp();
     if (lane < 3) {  // farm-level rings: mean ws, mean wd, sum power (MesClass.py:589-591)
       const int c = lane == 2 ? 3 : lane;
-      auto g = [&](int k) { return (double)s_val[c][k]; };
+      auto g = [&](int k) { return (double)s_push[c][k]; };
       const double sum = pairwise_sum(g, 0, T);
       const float v = (float)(lane == 2 ? sum : sum / T);
       const int o = d.farm_off[lane] + np % d.ch_H[c];
@@ -190,7 +207,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
   }
   __syncwarp();
 
-  if (a.flags & FIN_OBS) {  // farm_mes.get_measurements(scaled=True) + clip (MesClass.py:679-703, Wind_Farm_Env.py:513-520)
+  if (do_mes && (a.flags & FIN_OBS)) {  // farm_mes.get_measurements(scaled=True) + clip (MesClass.py:679-703, Wind_Farm_Env.py:513-520)
     const int n_out = d.obs_rows * d.obs_dim;
     for (int o = lane; o < n_out; o += 32) {
       const ObsDesc ds = d.obs_desc[o];
@@ -230,7 +247,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     }
   }
 
-  if ((a.flags & FIN_REWARD) && lane == 0) {
+  if (do_pow && (a.flags & FIN_REWARD) && lane == 0) {
     const int PA = d.power_avg;
     const int nfp = min(nfp_tot, PA), nbp = min(nbp_tot, PA);
     bool nan_seen = false;
@@ -274,7 +291,7 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32, 8) wg_finish_kernel(const D
     if (lane == 0) {
       __threadfence_system();
       const unsigned t = atomicAdd(a.done_count, 1u);
-      if (t == (unsigned)d.Bg - 1u) {
+      if (t == (unsigned)d.Bg * (PAIR ? 2u : 1u) - 1u) {
         *a.done_count = 0u;
         __threadfence_system();
         *a.done_flag = a.seq;
@@ -332,37 +349,45 @@ __global__ void wg_reset_init_kernel(const Dev d, const ResetDevArgs a) {
   }
 }
 
+template <bool LEAN, bool PAIR>
+static cudaError_t launch_finish_as(const Dev& d, const FinishArgs& a, cudaStream_t s, size_t smem, int dev) {
+  static size_t configured_dev[WG_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
+  size_t& configured = configured_dev[dev];
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true, LEAN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS, block = WG_FIN_WARPS * 32 * (PAIR ? 2 : 1);
+  if (a.pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, wg_finish_kernel<true, LEAN, PAIR>, d, a);
+  }
+  wg_finish_kernel<true, LEAN, PAIR><<<grid, block, smem, s>>>(d, a);
+  return cudaGetLastError();
+}
+
+// envs of one wave of the two-warps-per-env variant (4 CTAs of 4 envs per SM on 148 SMs): below this the kernel is pure
+// latency and the variant pays; above it the one-warp variant keeps the whole batch in a single wave
+#define WG_FIN_PAIR_MAX 2048
+
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(float) * WG_FIN_WARPS * (((size_t)d.ring_floats + 2 * (size_t)d.power_avg + 3) & ~(size_t)3);
-  const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
   if (smem <= 100 * 1024) {
-    static size_t configured_dev[WG_MAX_DEVICES] = {};  // per device: the opt-in is a per-device function attribute
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= WG_MAX_DEVICES) dev = 0;
-    size_t& configured = configured_dev[dev];
-    if (smem > 48 * 1024 && smem > configured) {
-      cudaError_t e = cudaFuncSetAttribute(wg_finish_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(wg_finish_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      configured = smem;
-    }
-    if (a.pdl) {
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WG_FIN_WARPS * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      at[0].val.programmaticStreamSerializationAllowed = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      return d.fin_lean ? cudaLaunchKernelEx(&cfg, wg_finish_kernel<true, true>, d, a)
-                        : cudaLaunchKernelEx(&cfg, wg_finish_kernel<true, false>, d, a);
-    }
-    if (d.fin_lean) wg_finish_kernel<true, true><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
-    else wg_finish_kernel<true, false><<<grid, WG_FIN_WARPS * 32, smem, s>>>(d, a);
-  } else {
-    wg_finish_kernel<false, false><<<grid, WG_FIN_WARPS * 32, 0, s>>>(d, a);
+    const bool pair = d.Bg <= WG_FIN_PAIR_MAX && smem <= 48 * 1024;
+    if (pair) return d.fin_lean ? launch_finish_as<true, true>(d, a, s, smem, dev) : launch_finish_as<false, true>(d, a, s, smem, dev);
+    return d.fin_lean ? launch_finish_as<true, false>(d, a, s, smem, dev) : launch_finish_as<false, false>(d, a, s, smem, dev);
   }
+  const int grid = (d.Bg + WG_FIN_WARPS - 1) / WG_FIN_WARPS;
+  wg_finish_kernel<false, false, false><<<grid, WG_FIN_WARPS * 32, 0, s>>>(d, a);
   return cudaGetLastError();
 }
 
@@ -452,8 +477,10 @@ cudaError_t launch_order(const Dev& d, cudaStream_t s) {
 //  * fewer farms than resident CTA slots (a GPU's share of a sharded batch, e.g. 512 envs): the farms are cut into
 //    parts of at most q tiles, q the smallest value whose part count fits the slots -- one wave that fills the
 //    machine, every CTA about equally long, instead of one CTA per farm with the launch as long as the heaviest farm;
-//  * more farms than slots: one CTA per farm, heaviest first; optionally the lightest `tail_units` farms, launched
-//    last, in `tail_parts` parts each, so that the grid drains on short CTAs.
+//  * between one and two waves of farms (e.g. 1024 envs on 888 slots): parts of at most q tiles that make up TWO full
+//    waves, instead of one full wave and a nearly empty one;
+//  * more farms: one CTA per farm, heaviest first; optionally the lightest `tail_units` farms, launched last, in
+//    `tail_parts` parts each, so that the grid drains on short CTAs.
 // Any split gives bit-identical results (fixed-point rotor sums, flow.cu).  One CTA; counting sort by tiles per part.
 #define WG_PLAN_BINS 1024
 __device__ __forceinline__ int plan_block_sum(int v, int* red) {  // all 1024 threads
@@ -500,14 +527,14 @@ __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ l
   const int tid = threadIdx.x;
   auto tiles = [&](int u) { return min(max((max(load[u], 0) + WG_TILE - 1) / WG_TILE, 1), WG_PLAN_BINS - 1); };
   int q = WG_PLAN_BINS;  // tiles per part; >= every farm's tiles: no split
-  if (U < p.slots) {
+  if (p.target > 0) {
     int lo = 1, hi = WG_PLAN_BINS - 1;
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       int n = 0;
       for (int u = tid; u < U; u += blockDim.x) n += min((tiles(u) + mid - 1) / mid, WG_MAX_PARTS);
       n = plan_block_sum(n, wsum);
-      if (n <= p.slots) hi = mid; else lo = mid + 1;
+      if (n <= p.target) hi = mid; else lo = mid + 1;
     }
     q = lo;
   }
@@ -518,7 +545,7 @@ __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ l
   __syncthreads();
   plan_exclusive_scan(hist, wsum);
   auto parts_of = [&](int u, int t) {
-    if (U < p.slots) return min((t + q - 1) / q, WG_MAX_PARTS);
+    if (p.target > 0) return min((t + q - 1) / q, WG_MAX_PARTS);
     const bool tail = p.tail_parts > 1 && hist[WG_PLAN_BINS - 1 - t] >= U - p.tail_units;
     return tail ? min(p.tail_parts, WG_MAX_PARTS) : 1;
   };

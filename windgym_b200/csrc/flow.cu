@@ -623,9 +623,9 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
     g_yaw = d.yaw[it]; g_der = d.derate[it];
     g_u = d.u[it]; g_v = d.v[it]; g_w = d.w[it]; g_pw = d.power[it]; g_ct = d.ct[it];
     g_head = d.head[it]; g_count = d.count[it]; g_retire = d.retire[it];
-    if (take_action) {
-      g_act = a.actions[b * T * d.act_var + tid];
-      if (d.act_var == 2) g_act2 = a.actions[b * T * 2 + T + tid];
+    if (take_action) {  // issued HERE (volatile: not sunk to the first use in the epilogue), consumed behind the tile loop
+      asm volatile("ld.global.f32 %0, [%1];" : "=f"(g_act) : "l"(a.actions + b * T * d.act_var + tid));
+      if (d.act_var == 2) asm volatile("ld.global.f32 %0, [%1];" : "=f"(g_act2) : "l"(a.actions + b * T * 2 + T + tid));
     }
   }
   if (tab_mine) { g_tws = d.tab_ws[tid]; g_tp = d.tab_p[tid]; g_tct = d.tab_ct[tid]; }
@@ -660,20 +660,6 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
     sh.ord[tid] = g_ord;
     float yaw = g_yaw;
     der_r = g_der;
-    if (take_action) {  // _adjust_yaws, Wind_Farm_Env.py:822-864
-      d.old_yaw[b * T + tid] = yaw;
-      const float act = g_act;
-      if (d.act_var == 2) {  // extension: induction (derating) action, applied as set point
-        der_r = fminf(fmaxf(d.derate_min + 0.5f * (g_act2 + 1.f) * (1.f - d.derate_min), d.derate_min), 1.f);
-      }
-      if (d.action_method == 0) {
-        yaw = fminf(fmaxf(yaw + act * d.yaw_step, d.yaw_min), d.yaw_max);
-      } else {
-        float tgt = (act + 1.0f) / 2.0f * (d.yaw_max - d.yaw_min) + d.yaw_min;
-        tgt = fminf(fmaxf(tgt, yaw - d.yaw_step), yaw + d.yaw_step);
-        yaw = fminf(fmaxf(tgt, d.yaw_min), d.yaw_max);
-      }
-    }
     sh.yaw[tid] = yaw;
     sh.u[tid] = g_u;
     sh.v[tid] = g_v;
@@ -1046,6 +1032,23 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
         u += (float)sh.acc_ad[tid] * WG_FX_INV;
         v += (float)sh.acc_ad[TC + tid] * WG_FX_INV;
         w += (float)sh.acc_ad[2 * TC + tid] * WG_FX_INV;
+      }
+      // _adjust_yaws (Wind_Farm_Env.py:822-864), once per env step.  The actions were requested in the prologue and
+      // are first needed here, behind the tile loop: when they come from mapped host memory (wg_step_host) the PCIe
+      // read latency is off every CTA's critical path.  (Nothing in the tile loop reads the yaw.)
+      if (sub == 0 && take_action) {
+        float yaw0 = sh.yaw[tid];
+        d.old_yaw[b * T + tid] = yaw0;
+        if (d.act_var == 2)  // extension: induction (derating) action, applied as set point
+          der_r = fminf(fmaxf(d.derate_min + 0.5f * (g_act2 + 1.f) * (1.f - d.derate_min), d.derate_min), 1.f);
+        if (d.action_method == 0) {
+          yaw0 = fminf(fmaxf(yaw0 + g_act * d.yaw_step, d.yaw_min), d.yaw_max);
+        } else {
+          float tgt = (g_act + 1.0f) / 2.0f * (d.yaw_max - d.yaw_min) + d.yaw_min;
+          tgt = fminf(fmaxf(tgt, yaw0 - d.yaw_step), yaw0 + d.yaw_step);
+          yaw0 = fminf(fmaxf(tgt, d.yaw_min), d.yaw_max);
+        }
+        sh.yaw[tid] = yaw0;
       }
       const float yaw = sh.yaw[tid];
       float sg, cg;

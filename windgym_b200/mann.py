@@ -155,7 +155,8 @@ class MannBox:
     @classmethod
     def from_file(cls, path, device="cuda:0", dxyz=None, lowpass_width=160.0):
         """``MannTurbulenceField.from_netcdf`` (Wind_Farm_Env.py:614-617).  ``.npy`` ([3,Nx,Ny,Nz], needs ``dxyz``),
-        ``.npz`` (arrays ``uvw`` and ``dxyz``) or NetCDF-3 through scipy (variables ``uvw`` + coordinate axes)."""
+        ``.npz`` (arrays ``uvw`` and ``dxyz``), NetCDF-3 through scipy, or NetCDF-4 / HDF5 as hipersim writes it through the
+        built-in reader ``windgym_b200.hdf5_min`` (contiguous / chunked / deflate-compressed numeric datasets)."""
         path = str(path)
         if path.endswith(".npy"):
             uvw, d = np.load(path), dxyz
@@ -163,14 +164,16 @@ class MannBox:
             z = np.load(path)
             uvw, d = z["uvw"], tuple(z["dxyz"]) if "dxyz" in z.files else dxyz
         else:
-            try:
+            with open(path, "rb") as fh:
+                magic = fh.read(8)
+            if magic[:3] == b"CDF":          # classic NetCDF-3
                 from scipy.io import netcdf_file
                 with netcdf_file(path, "r", mmap=False) as nc:
                     uvw = np.array(nc.variables["uvw"][:])
                     d = tuple(float(nc.variables[a][1] - nc.variables[a][0]) for a in ("x", "y", "z"))
-            except Exception as e:
-                raise NotImplementedError(f"cannot read turbulence box {path!r}: NetCDF-4/HDF5 boxes need to be "
-                                          f"converted to .npz (uvw, dxyz) first ({e})")
+            else:                            # NetCDF-4 = HDF5: the built-in minimal reader (windgym_b200/hdf5_min.py)
+                from .hdf5_min import read_mann_box
+                uvw, d = read_mann_box(path)
         if d is None:
             raise ValueError("dxyz is required for a bare .npy box")
         return cls(torch.as_tensor(np.ascontiguousarray(uvw), device=torch.device(device)), d, lowpass_width=lowpass_width)
