@@ -480,7 +480,9 @@ cudaError_t launch_order(const Dev& d, cudaStream_t s) {
 //  * between one and two waves of farms (e.g. 1024 envs on 888 slots): parts of at most q tiles that make up TWO full
 //    waves, instead of one full wave and a nearly empty one;
 //  * more farms: one CTA per farm, heaviest first; optionally the lightest `tail_units` farms, launched last, in
-//    `tail_parts` parts each, so that the grid drains on short CTAs.
+//    `tail_parts` parts each, so that the grid drains on short CTAs;
+//  * large farms (64-turbine variant: 100-250 tiles per farm): no part longer than `max_tiles` tiles in any regime --
+//    a CTA of ~45 tiles runs ~100 us, the per-CTA overhead is negligible and many short CTAs pack and drain better.
 // Any split gives bit-identical results (fixed-point rotor sums, flow.cu).  One CTA; counting sort by tiles per part.
 #define WG_PLAN_BINS 1024
 __device__ __forceinline__ int plan_block_sum(int v, int* red) {  // all 1024 threads
@@ -521,7 +523,7 @@ __device__ __forceinline__ void plan_exclusive_scan(int* hist, int* wsum) {  // 
   __syncthreads();
 }
 __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ load, int U, PlanArgs p,
-                                                       int2* __restrict__ work) {
+                                                       int2* __restrict__ work, int* __restrict__ flags) {
   __shared__ int hist[WG_PLAN_BINS];
   __shared__ int wsum[32];
   const int tid = threadIdx.x;
@@ -545,9 +547,11 @@ __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ l
   __syncthreads();
   plan_exclusive_scan(hist, wsum);
   auto parts_of = [&](int u, int t) {
-    if (p.target > 0) return min((t + q - 1) / q, WG_MAX_PARTS);
-    const bool tail = p.tail_parts > 1 && hist[WG_PLAN_BINS - 1 - t] >= U - p.tail_units;
-    return tail ? min(p.tail_parts, WG_MAX_PARTS) : 1;
+    int n = 1;
+    if (p.target > 0) n = (t + q - 1) / q;
+    else if (p.tail_parts > 1 && hist[WG_PLAN_BINS - 1 - t] >= U - p.tail_units) n = p.tail_parts;
+    if (p.max_tiles > 0) n = max(n, (t + p.max_tiles - 1) / p.max_tiles);
+    return min(n, WG_MAX_PARTS);
   };
   int np_mine[8], t_mine[8];  // up to 8192 farms per handle go through registers; more are recomputed
   for (int k = 0, u = tid; u < U && k < 8; ++k, u += blockDim.x) { t_mine[k] = tiles(u); np_mine[k] = parts_of(u, t_mine[k]); }
@@ -572,10 +576,11 @@ __global__ void __launch_bounds__(1024) wg_plan_kernel(const int* __restrict__ l
   // after the scatter the last bin's counter is the number of entries written
   const int total = hist[WG_PLAN_BINS - 1];
   for (int i = total + tid; i < p.n_work; i += blockDim.x) work[i] = make_int2(-1, 0);
+  if (tid == 0 && total > p.n_work) atomicOr(flags, 4);  // cannot happen by construction (api.cu sizes the table); loud if it does
 }
 
 cudaError_t launch_plan(const Dev& d, const PlanArgs& p, cudaStream_t s) {
-  wg_plan_kernel<<<1, 1024, 0, s>>>(d.load, d.Bg * d.F, p, d.work);
+  wg_plan_kernel<<<1, 1024, 0, s>>>(d.load, d.Bg * d.F, p, d.work, d.flags);
   return cudaGetLastError();
 }
 

@@ -429,9 +429,19 @@ __device__ __forceinline__ LaneLoc locate(const SH& sh, int tile, int lane, int 
     const unsigned full = 0xffffffffu;
     const int pre_hi = lane < T ? sh.pre[lane + 1] : 0x7fffffff;
     const int c0 = __popc(__ballot_sync(full, pre_hi <= f0));
-    const int c1 = __popc(__ballot_sync(full, pre_hi <= min(f0 + WG_TILE - 1, ntot - 1)));
-    lo = c0;
-    for (int c = c0; c < c1; ++c) lo += (fl >= __shfl_sync(full, pre_hi, c)) ? 1 : 0;
+    // chain ends inside the tile, as a bit mask over the tile's lanes: lane k (a chain) sets bit pre[k+1] - f0 when that
+    // lies in (0, 31]; a station at lane L has passed every end at a position <= L.  One warp-wide OR instead of a
+    // data-dependent shuffle loop (which the compiler turned into ~400 instructions per tile).  Empty chains make two
+    // ends coincide on one bit: then (rare: the first steps of a spin-up) the ends are counted one by one.
+    const unsigned rel = (unsigned)(pre_hi - f0);
+    const bool inside = rel - 1u < (unsigned)(WG_TILE - 1) && pre_hi <= ntot - 1;   // 1 <= rel <= 31, a station follows
+    const unsigned ends = __reduce_or_sync(full, inside ? 1u << rel : 0u);
+    const int n_in = __popc(__ballot_sync(full, inside));
+    lo = c0 + __popc(ends & (0xffffffffu >> (31 - lane)));
+    if (n_in != __popc(ends)) {  // coinciding ends (warp-uniform branch)
+      lo = c0;
+      for (int c = c0; c < c0 + n_in; ++c) lo += (fl >= __shfl_sync(full, pre_hi, c)) ? 1 : 0;
+    }
     const int base = __shfl_sync(full, pre_hi, max(lo - 1, 0));
     L.q = fl - (lo > 0 ? base : 0);
   } else {

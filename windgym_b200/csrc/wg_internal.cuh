@@ -139,6 +139,7 @@ struct PlanArgs {
   int n_work;      // table entries (= CTAs launched); unused ones are marked -1
   int slots;       // resident CTAs of the flow kernel on this device
   int target;      // > 0: cut the farms into about `target` parts of equal size (one or two full waves of CTAs)
+  int max_tiles;   // > 0: no part longer than this many tiles (large farms: many short CTAs pack and drain better)
   int tail_units;  // more farms than slots: the lightest tail_units farms (launched last) are cut into
   int tail_parts;  //   tail_parts parts each, so that the grid drains on short CTAs (1: no tail split)
 };

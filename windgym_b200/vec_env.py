@@ -484,6 +484,8 @@ class VecWindFarmEnv:
             raise Exception("NaN Power")
         if bool((fl & 2).any()):
             raise _lib.WgError("wake particle chain overflow (p_cap too small)")
+        if bool((fl & 4).any()):
+            raise _lib.WgError("work table overflow in wg_plan_kernel: farms were left unstepped (library bug)")
 
     def _info(self):
         """Device views with the reference's info keys (Wind_Farm_Env.py:527-555); zero-copy, no sync.  The views
