@@ -286,10 +286,15 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32 * (PAIR ? 2 : 1), PAIR ? 4 :
     if (a.reward_h) { a.reward_h[b] = (float)rew; a.truncated_h[b] = tr; }
     d.timestep[b] = ts + 1;
   }
-  if (a.done_flag) {  // host-visible completion: the warp's host stores, ONE system fence (lane 0: the warp barrier
-    __syncwarp();     // orders the other lanes' stores before it, the fence is cumulative), one arrival per env
+  if (a.done_flag) {
+    // Host-visible completion.  Every warp orders its host stores at device scope (warp barrier, then lane 0's
+    // __threadfence: cheap) and arrives on a device counter; the LAST warp to arrive issues the one system-scope fence
+    // -- cumulative over everything it has observed through the counter, i.e. all warps' stores -- and publishes the
+    // step's sequence number.  (A system fence per warp was the top stall of this kernel in the zero-copy path: ncu
+    // profiles/r05n_finish512_ncu_summary.txt, membar 13.5 stall cycles per issued instruction.)
+    __syncwarp();
     if (lane == 0) {
-      __threadfence_system();
+      __threadfence();
       const unsigned t = atomicAdd(a.done_count, 1u);
       if (t == (unsigned)d.Bg * (PAIR ? 2u : 1u) - 1u) {
         *a.done_count = 0u;

@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
         count_below2(sh.xs, xs_top, xn, xe, cn, ce);
       };
       if (!TURB) move_and_search();
-      if (TURB && Lc.valid) prefetch_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo);
+      if (TURB && tile == tile0 && Lc.valid) prefetch_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo);  // later tiles: a round ahead
       WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches, moves, plane searches
       mbar_wait(bar, phase);
       phase ^= 1u;
@@ -957,7 +957,14 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
       }
       __syncwarp();
       WG_PHASE(4)  // store issue + superposition
+      // Turbulence box: the next tile's wake-centre bricks are pulled towards L2 one round ahead.  The next tile's
+      // positions were prefetched to L2 at the top of this round; reading them is an L2 hit that overlaps the wait for
+      // the store, and the random DRAM read of the brick then has the whole tile set-up of the next round to land.
+      float4 pnx = make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool pf_next = TURB && tile + tstride < ntiles && Ln.valid;
+      if (pf_next) pnx = __ldcg(reinterpret_cast<const float4*>(pm_old + (unsigned)(Ln.chain * P + Ln.slot) * 4u));
       bulk_wait_read0();  // the store has drained its shared-memory reads: the buffer can be refilled
+      if (pf_next) prefetch_lp(d, pnx.x, pnx.y, pnx.z, xs_t, tb_yo, tb_zo);
       __syncwarp();
       WG_PHASE(5)  // waiting for the store to release the buffer
     }
@@ -1005,7 +1012,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
       }
       if (tid == 0) d.part_arrive[bf] = 0;
     }
-    if (TURB) {  // ambient fluctuation averaged over every rotor's quadrature points at the new time level
+    if (TURB) {
+      // Ambient fluctuation averaged over every rotor's quadrature points at the new time level.  (Sampling it at the
+      // head of the step, together with the isotropic box, was measured slower -- 0.566 vs 0.549 ms per launch: there
+      // every warp waits for the random reads before its first tile, here the warps that finish early absorb them.)
       for (int idx = tid; idx < T * WG_NQ; idx += blockDim.x) {  // T*16: half-warps stay whole
         const int t = idx >> 4;
         const float4 q = sample_raw(d, sh.xr[t], fmaf(qy, R, sh.yr[t]), fmaf(qz, R, d.zh), xs_t1, tb_yo, tb_zo, tb_sc);
