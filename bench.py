@@ -418,7 +418,7 @@ def run_gpu(a):
         prng = np.random.default_rng(rank)
         tmax = pool.time_max.cpu().numpy() if torch.is_tensor(pool.time_max) else pool.time_max
         pool.state["timestep"][:] = torch.as_tensor((prng.uniform(0, 1, B) * tmax).astype(np.int32), device=dev)
-        for i in range(120 if device_side else 10):          # the spares' first spin-up completes in the background
+        for i in range(120):                                 # the spares' first spin-up completes in the background
             genv.step(acts_dev[i % (W + K)])
         barrier()
         n_res = torch.zeros((), dtype=torch.int64, device=dev)

@@ -9,9 +9,9 @@ This is the oracle that travels to the GPU box (``/root/reference`` does not).  
 * baseline yaw controllers                     -- ``WindGym/BasicControllers/BasicControllers.py:10-73``
 * multi-agent observation split                -- ``WindGym/WindEnvMulti.py:79-103``
 
-over the flow seam in ``oracle.dwm_numpy``.  It is PINNED: ``tests/test_oracle_vs_reference.py`` (build
-container) runs the unmodified reference files next to it, and ``tests/golden/*.npz`` carries the reference's
-outputs to the GPU box.  Deliberate differences from the reference: wind conditions / initial yaws can be
+over the flow seam in ``oracle.dwm_numpy``.  It is PINNED: ``tests/golden/make_golden.py`` (build container) runs the
+unmodified reference files through ``oracle/ref_loader.py`` and writes their outputs to ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` compares this module with them bit for bit, anywhere (the fixtures travel to the GPU box).  Deliberate differences from the reference: wind conditions / initial yaws can be
 injected (the batched tests feed identical per-env values to both sides); the measurement-noise RNG is seeded
 (the reference's is not); after truncation the object stays usable (Q11).
 """

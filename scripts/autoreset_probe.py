@@ -1,28 +1,56 @@
-"""Throughput with auto-reset (SURVEY.md 8d metric (ii)): naive masked reset vs the spare-env pool."""
-import sys, time, numpy as np, torch
-sys.path.insert(0, '.')
-import bench
-from windgym_b200 import V80, VecWindFarmEnv, PooledVecEnv
-from windgym_b200.vector import GymVectorEnv
-B, T = 4096, 16
-cfg = bench.workload_config(4, 4, "Power_avg")
-mode = sys.argv[1] if len(sys.argv) > 1 else "pool"
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 400
-if mode == "pool":
-    venv = PooledVecEnv(V80(), B, reserve=int(sys.argv[3]) if len(sys.argv) > 3 else 512, config=cfg, device="cuda:0", n_passthrough=5, seed=0)
-else:
-    venv = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", n_passthrough=5, seed=0)
-env = GymVectorEnv(venv=venv, as_torch=True)
-t0 = time.perf_counter(); env.reset(seed=0); torch.cuda.synchronize(); print("full reset s", time.perf_counter() - t0)
-acts = torch.rand((B, T), device="cuda:0") * 2 - 1
-rng = np.random.default_rng(0)
-venv.state["timestep"][:] = torch.as_tensor((rng.uniform(0, 1, B) * venv.time_max).astype(np.int32), device="cuda:0")
-for i in range(20):
-    env.step(acts)
-ndone = 0
-torch.cuda.synchronize(); t0 = time.perf_counter()
-for i in range(n):
-    obs, r, term, trunc, infos = env.step(acts)
-    ndone += int(trunc.sum())
-torch.cuda.synchronize(); dt = time.perf_counter() - t0
-print(f"autoreset {mode}: {B*n/dt:.0f} env-steps/s, {dt/n*1e3:.3f} ms/step, {ndone} resets in {n} steps", getattr(venv, "stats", ""))
+"""Auto-reset throughput of the two pools on the bench workload: scripts/autoreset_probe.py [envs] [device|host|both]"""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from windgym_b200 import DevicePooledVecEnv, PooledVecEnv, V80  # noqa: E402
+from windgym_b200.vector import GymVectorEnv  # noqa: E402
+
+
+def leg(B, device_side, steps):
+    cfg = bench.workload_config(4, 4, "Power_avg")
+    dev = torch.device("cuda:0")
+    cls = DevicePooledVecEnv if device_side else PooledVecEnv
+    R = max(384 if device_side else 64, B // 8)
+    pool = cls(V80(), B, reserve=R, config=cfg, device="cuda:0", n_passthrough=5, seed=0)
+    genv = GymVectorEnv(venv=pool, as_torch=True)
+    genv.reset(seed=0)
+    acts = (torch.rand((64, B, 16), generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
+    tmax = pool.time_max.cpu().numpy() if torch.is_tensor(pool.time_max) else pool.time_max
+    pool.state["timestep"][:] = torch.as_tensor((np.random.default_rng(0).uniform(0, 1, B) * tmax).astype(np.int32), device=dev)
+    for i in range(120 if device_side else 10):
+        genv.step(acts[i % 64])
+    torch.cuda.synchronize()
+    n = torch.zeros((), dtype=torch.int64, device=dev)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, _, _, tr, _ = genv.step(acts[i % 64])
+        if device_side:
+            n += tr.sum()
+        else:
+            n += int(tr.sum())
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"{'device' if device_side else 'host'} pool, {B} envs: {B * steps / dt / 1e6:.2f} M env-steps/s, {1e3 * dt / steps:.3f} ms/step, "
+          f"episodes {int(n)}, stats {dict(pool.stats)}")
+    pool.close()
+    del genv, pool
+    torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    which = sys.argv[2] if len(sys.argv) > 2 else "both"
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 400
+    if which in ("host", "both"):
+        leg(B, False, min(steps, 300))
+    if which in ("device", "both"):
+        leg(B, True, steps)
+    if which == "both":
+        leg(B, False, min(steps, 300))

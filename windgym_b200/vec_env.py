@@ -324,11 +324,11 @@ class VecWindFarmEnv:
             if turb_offset is not None:
                 self.turb_offset[sel] = np.broadcast_to(np.asarray(turb_offset, dtype=np.float64), (B, 3))[sel]
             elif B > 1:            # a lone env sits at the box origin like the reference's single simulation
+                # one stream per env, [seed ^ salt, env, episode] -- evaluated for all envs of the reset at once
+                # (fast_rng: numpy's SeedSequence + PCG64 with array arithmetic), not one Generator object per env
                 L = np.array(self.turb_box.Nxyz) * np.array(self.turb_box.dxyz)
-                for i in sel:
-                    r = np.random.default_rng([0 if seed is None else int(seed), int(i), self._episode,
-                                               int(self._tf_seed[i]), 12345])
-                    self.turb_offset[i] = r.uniform(0.0, L)
+                s32 = ((0 if seed is None else int(seed)) ^ 0x5EEDB0C5 ^ (int(self._tf_seed[sel].sum()) * 2654435761)) & 0xFFFFFFFF
+                self.turb_offset[sel] = uniform_streams(s32, sel, self._episode & 0xFFFFFFFF, 3) * L
             tb = dict(off=self.turb_offset, scale=self.turb_box.scale_for(ti, ws))
         f32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32)).to(dev, non_blocking=True)
         i32 = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev, non_blocking=True)
