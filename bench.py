@@ -487,6 +487,13 @@ def run_gpu(a):
         except Exception:
             pass
         r["traffic"], r["traffic_source"] = traffic, traffic_src
+        # SURVEY.md 8(d) sizes its state model at N_p = 804 stations per 4x4 farm (16 m spacing, wd = 270); the frozen
+        # specification releases a particle every ceil(16 m / (ws dt)) steps and holds fewer (the
+        # rotor powers move by < 1e-4 between the two spacings).  Time is proportional to stations: the same kernel on
+        # the SURVEY's state model would deliver value x live / 804.
+        if (a.nx, a.ny) == (4, 4):
+            r["survey_np"] = 804
+            r["value_at_survey_np_equiv"] = m["value"] * min(1.0, r["live_stations_per_env_farm"] / 804.0)
         line = {
             "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": scaling,

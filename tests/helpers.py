@@ -61,11 +61,11 @@ def oracle_rollout(cfg, ws, ti, wd, yaw0, acts, multi=False, reset_kw=None, **kw
     """Run the CPU oracle env for every batch entry.  acts: [steps, B, T].  Returns per-env stacked arrays."""
     B = len(ws)
     out = {k: [] for k in ("obs0", "obs", "reward", "power", "yaw", "ws_turb", "trunc", "power_base", "yaw_base",
-                           "time_max", "t_developed")}
+                           "time_max", "t_developed", "u")}
     for b in range(B):
         env = WindFarmEnvOracle(OracleV80(), cfg, reset_init=False, **kw)
         o0, _ = env.reset(wind=(ws[b], ti[b], wd[b]), yaw0=yaw0[b], **(reset_kw or {}))
-        rec = {k: [] for k in ("obs", "reward", "power", "yaw", "ws_turb", "trunc", "power_base", "yaw_base")}
+        rec = {k: [] for k in ("obs", "reward", "power", "yaw", "ws_turb", "trunc", "power_base", "yaw_base", "u")}
         if multi:
             o0 = np.stack(env.mes.get_multi())
         for a in acts[:, b]:
@@ -75,6 +75,7 @@ def oracle_rollout(cfg, ws, ti, wd, yaw0, acts, multi=False, reset_kw=None, **kw
             rec["obs"].append(o); rec["reward"].append(r); rec["trunc"].append(tr)
             rec["power"].append(info["Power pr turbine agent"]); rec["yaw"].append(info["yaw angles agent"])
             rec["ws_turb"].append(info["Wind speed at turbines"])
+            rec["u"].append(np.array(env.fs.windTurbines.rotor_avg_windspeed[:, 0]))
             if env.Baseline_comp:
                 rec["power_base"].append(info["Power pr turbine baseline"]); rec["yaw_base"].append(info["yaw angles base"])
         out["obs0"].append(o0)

@@ -159,7 +159,7 @@ void pin_turbulence_in_l2(wg_handle* h, cudaStream_t s) {
   X(spin, int, "spin") X(xr, float, "xr") X(yr, float, "yr") X(xs_sorted, float, "xs_sorted")                           \
   X(ord_sorted, int, "ord_sorted") X(meas, float, "meas") X(base_pow_mean, float, "base_pow_mean")                      \
   X(old_yaw, float, "old_yaw") X(rings, float, "rings") X(tb_off, float, "tb_off") X(tb_scale, float, "tb_scale")       \
-  X(fp_ring, float, "farm_pow_ring") X(bp_ring, float, "base_pow_ring")
+  X(fp_ring, float, "farm_pow_ring") X(bp_ring, float, "base_pow_ring") X(fp_ring_lo, float, "farm_pow_ring_lo")
 
 void resolve_state_offsets(wg_handle* h) {
   h->state_off.clear();
@@ -393,6 +393,7 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   add_field(h, "tb_scale", 0, {B});
   add_field(h, "rings", 0, {B, off});
   add_field(h, "farm_pow_ring", 0, {B, cfg->power_avg});
+  add_field(h, "farm_pow_ring_lo", 0, {B, cfg->power_avg});
   add_field(h, "base_pow_ring", 0, {B, cfg->power_avg});
   // field table of the env-copy kernel: leading dimension B, or [2, B, ...] for the ping-pong buffer
   std::vector<wg::CopyField> cf;

@@ -160,9 +160,12 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32 * (PAIR ? 2 : 1), PAIR ? 4 :
   if (do_pow && (a.flags & FIN_PUSH_FP)) {  // farm_pow_deq.append(mean_power.sum()) (Wind_Farm_Env.py:975-977): noise-free means
     if (lane == 0) {
       auto gp = [&](int k) { return (double)s_val[3][k]; };
-      const float v = (float)pairwise_sum(gp, 0, T);
+      const double vd = pairwise_sum(gp, 0, T);
+      const float v = (float)vd;
       fp[nfp_tot % d.power_avg] = v;
       if (STAGE) g_fp[nfp_tot % d.power_avg] = v;
+      if (!LEAN && d.power_reward == 3)  // Power_diff: keep what float32 drops
+        d.fp_ring_lo[(size_t)b * d.power_avg + nfp_tot % d.power_avg] = (float)(vd - (double)v);
       d.n_fp[b] = nfp_tot + 1;
     }
     nfp_tot += 1;
@@ -262,7 +265,8 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32 * (PAIR ? 2 : 1), PAIR ? 4 :
       rew = (sfp / nfp) / T / (double)g_rated;
     } else if (!LEAN && d.power_reward == 3) {  // Power_diff over the logical (oldest -> newest) order of the deque
       const int ws_ = PA / 10, ntot = nfp_tot;
-      auto lg = [&](int k) { return (double)fp[(ntot - nfp + k) % PA]; };
+      const float* fplo = d.fp_ring_lo + (size_t)b * PA;
+      auto lg = [&](int k) { const int i = (ntot - nfp + k) % PA; return (double)fp[i] + (double)fplo[i]; };
       double latest = 0.0, oldest = 0.0;
       int nl = 0, no = 0;
       for (int k = PA - ws_; k < PA && k < nfp; ++k) { latest += lg(k); ++nl; }

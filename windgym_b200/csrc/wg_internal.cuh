@@ -101,6 +101,8 @@ struct Dev {
   float *old_yaw;         // [B,T]
   float *rings;           // [B,ring_floats]
   float *fp_ring, *bp_ring;  // [B,power_avg]
+  float *fp_ring_lo;         // [B,power_avg] float32 remainder of the farm power sums (value = fp_ring + fp_ring_lo): the
+                             // Power_diff reward is a DIFFERENCE of window means of ~1e7 W values (Wind_Farm_Env.py:904-918)
   // ambient turbulence box shared by all envs of the handle (null: uniform inflow); per-env offset and scale
   const float4* tb_raw;   // [Nx,Ny,Nz] (u, v, w, 0)
   const float2* tb_lp;    // [Nx,Ny,Nz] (v, w) low-pass filtered in y, z: moves the wake centres
