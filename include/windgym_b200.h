@@ -161,6 +161,11 @@ int wg_mes_push_extract(wg_handle* h, void* state, const float* ws, const float*
  * wg_copy_envs: copy the complete per-env state of slot src[k] into slot dst[k] (src, dst: device int32 [n]) --
  * swap a pre-developed spare env in for an env whose episode just ended. */
 int wg_set_active(wg_handle* h, int32_t n_active);
+/* Fraction (0, 1] of the device's resident CTA slots wg_step plans its single-wave decomposition for (default 1).  A
+ * caller that keeps other work resident next to the stepping grid -- the background spin-ups of a spare pool hold one
+ * CTA per env for ~20 ms -- lowers it so that a small batch, which wg_step cuts into parts that fill the machine,
+ * still fits ONE wave of what is left. */
+int wg_set_slot_share(wg_handle* h, float share);
 int wg_copy_envs(wg_handle* h, void* state, const int32_t* src, const int32_t* dst, int32_t n, void* cuda_stream);
 
 /* Device-side auto-reset: the host is not in the loop.  wg_pool_init makes the slots [n_active, n_envs) a pool of

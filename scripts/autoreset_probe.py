@@ -18,7 +18,13 @@ def leg(B, device_side, steps):
     dev = torch.device("cuda:0")
     cls = DevicePooledVecEnv if device_side else PooledVecEnv
     R = max(384 if device_side else 64, B // 8)
-    pool = cls(V80(), B, reserve=R, config=cfg, device="cuda:0", n_passthrough=5, seed=0)
+    extra = {}
+    if device_side:
+        if os.environ.get("POOL_STREAMS"):
+            extra["n_streams"] = int(os.environ["POOL_STREAMS"])
+        if os.environ.get("POOL_EVERY"):
+            extra["refill_every"] = int(os.environ["POOL_EVERY"])
+    pool = cls(V80(), B, reserve=R, config=cfg, device="cuda:0", n_passthrough=5, seed=0, **extra)
     genv = GymVectorEnv(venv=pool, as_torch=True)
     genv.reset(seed=0)
     acts = (torch.rand((64, B, 16), generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
@@ -37,6 +43,29 @@ def leg(B, device_side, steps):
             n += int(tr.sum())
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    if os.environ.get("POOL_PROFILE"):      # per-kernel device time of the stepping kernels while the pool is working
+        inner = pool.inner
+        inner.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(256):
+            genv.step(acts[i % 64])
+        e1.record()
+        torch.cuda.synchronize()
+        fl, fi, n = inner.profile_read()
+        inner.profile_enable(False)
+        print(f"   while pooled: flow {1e3 * fl / n:.1f} us, finish {1e3 * fi / n:.1f} us per step; stepping stream busy "
+              f"{1e3 * e0.elapsed_time(e1) / 256:.1f} us per step")
+        # the swap + copy pair alone (nothing finished: flags cleared), back to back on the stepping stream
+        inner.truncated.zero_()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(256):
+            pool.lib.wg_pool_swap(inner._h, inner._step_ptrs[0], inner._step_ptrs[3], inner._step_ptrs[1],
+                                  pool.swapped.data_ptr(), pool._final.data_ptr(), inner._stream())
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"   wg_pool_swap alone (no episode finished): {1e3 * e0.elapsed_time(e1) / 256:.1f} us per call")
     print(f"{'device' if device_side else 'host'} pool, {B} envs: {B * steps / dt / 1e6:.2f} M env-steps/s, {1e3 * dt / steps:.3f} ms/step, "
           f"episodes {int(n)}, stats {dict(pool.stats)}")
     pool.close()

@@ -76,6 +76,7 @@ SYMBOLS = {
     "wg_mes_push_extract": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
     "wg_set_active": (C.c_int, [C.c_void_p, C.c_int32]),
+    "wg_set_slot_share": (C.c_int, [C.c_void_p, C.c_float]),
     "wg_copy_envs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_pool_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]),
     "wg_pool_refill": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(PoolDraw), C.c_void_p, C.c_int32, C.c_void_p]),

@@ -72,6 +72,8 @@ struct wg_handle {
   bool use_split = true;              // WG_NO_SPLIT=1: never cut a farm into parts
   int max_part_tiles = 0;             // WG_MAX_PART_TILES (0: off): longest part of a large farm, in tiles.  Measured on
                                       // cfg 4 (8x8, 1024 envs): 48 -> 0.609 ms, 24 -> 0.620 ms, off -> 0.587 ms per launch
+  float slot_share = 1.f;             // wg_set_slot_share / WG_SLOT_SHARE: fraction of the resident CTA slots the step plans for
+  int fill_waves = 0;                 // WG_FILL_WAVES=k: below k waves of farms, equalised parts that fill the last wave
   bool two_wave = true;               // WG_NO_TWOWAVE=1: between 1 and 2 waves of farms, keep one CTA per farm
   bool use_pdl = true;                // WG_NO_PDL=1: plain stream order between the flow and the finish kernel
   // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
@@ -430,6 +432,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   const char* f_br = getenv("WG_FORCE_BRICKS");
   h->force_bricks = f_br && f_br[0] == '1';
   if (const char* mt = getenv("WG_MAX_PART_TILES")) h->max_part_tiles = std::max(0, atoi(mt));
+  if (const char* fw = getenv("WG_FILL_WAVES")) h->fill_waves = std::max(0, atoi(fw));
+  if (const char* ss = getenv("WG_SLOT_SHARE")) h->slot_share = (float)atof(ss);
   const char* no_tw = getenv("WG_NO_TWOWAVE");
   h->two_wave = !(no_tw && no_tw[0] == '1');
   const char* no_pdl = getenv("WG_NO_PDL");
@@ -570,7 +574,12 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   const bool by_table = h->use_split && d.S == 1;
   if ((h->use_order || by_table) && (h->order_state != state || h->order_n != d.Bg || ++h->order_age >= WG_ORDER_PERIOD)) {
     if (by_table) {
-      if (h->slots <= 0) h->slots = wg::flow_resident_ctas(d);
+      if (h->slots <= 0) {
+        h->slots = wg::flow_resident_ctas(d);
+        // part of the machine is permanently taken by other work of the caller (background spin-ups of a spare pool:
+        // wg_set_slot_share): plan the stepping grid for the share that is left, so that it stays ONE wave
+        if (h->slot_share > 0.f && h->slot_share < 1.f) h->slots = std::max(1, (int)(h->slots * h->slot_share));
+      }
       const int U = d.Bg * d.F;
       wg::PlanArgs pa{};
       pa.slots = h->slots;
@@ -584,6 +593,8 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
         pa.target = pa.n_work = h->slots;
       } else if (U < 2 * h->slots && h->two_wave) {
         pa.target = pa.n_work = 2 * h->slots;
+      } else if (h->fill_waves > 0 && U < h->fill_waves * h->slots) {   // experiment: fill the last wave (WG_FILL_WAVES)
+        pa.target = pa.n_work = (U + h->slots - 1) / h->slots * h->slots;
       } else {
         pa.tail_units = std::min(h->tail_units, U);
         pa.tail_parts = pa.tail_units > 0 ? h->tail_parts : 1;
@@ -837,6 +848,14 @@ int wg_set_added_turbulence(wg_handle* h, const float* iso_uvw0, int32_t nx, int
   d.tb2_len_x = (float)((double)nx * (double)dx);
   d.k_m1 = k_m1; d.k_m2 = k_m2;
   h->slots = 0; h->order_state = nullptr;
+  return WG_OK;
+}
+
+int wg_set_slot_share(wg_handle* h, float share) {
+  if (!h) return fail(WG_ERR_INVALID, "wg_set_slot_share: null argument");
+  if (!(share > 0.f && share <= 1.f)) return fail(WG_ERR_INVALID, "wg_set_slot_share: share must be in (0, 1]");
+  h->slot_share = share;
+  h->slots = 0; h->order_state = nullptr;   // re-plan at the next step
   return WG_OK;
 }
 

@@ -678,45 +678,93 @@ __global__ void wg_pool_publish_kernel(const PoolDev p, int mask_row) {
   }
 }
 
-// One CTA.  (1) spares whose copy was issued in the previous step are free to be refilled; (2) ready spares and
-// finished episodes are collected in index order and paired; (3) swapped[b] = 1 for the envs that get a new episode
-// in this step -- an episode that finds no ready spare simply runs on and is paired in a later step.
-__global__ void __launch_bounds__(1024) wg_pool_swap_kernel(const Dev d, const PoolDev p, const uint8_t* __restrict__ truncated,
-                                                            uint8_t* __restrict__ swapped) {
-  __shared__ int scan[1024];
-  __shared__ int wsum[32];
+// One small CTA (256 threads, a few thousand registers: it fits next to whatever is resident -- a 1024-thread CTA
+// needs a whole SM's register file and waited tens of microseconds for one to drain while background spin-ups hold a
+// CTA on every SM).  (1) spares whose copy was issued in the previous step are free to be refilled; (2) ready spares
+// and finished episodes are collected IN INDEX ORDER (block scan, no atomics: the k-th ready spare goes to the k-th
+// finished env, run after run) and paired; (3) swapped[b] = 1 for the envs that get a new episode in this step -- an
+// episode that finds no ready spare simply runs on and is paired in a later step.  Every thread looks at 16
+// consecutive envs per pass (4-byte loads of the flag bytes), so 4096 envs are one pass.
+#define WG_SWAP_THREADS 256
+__device__ __forceinline__ int swap_block_excl_scan(int v, int* wsum, int& total) {  // all WG_SWAP_THREADS threads
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < WG_SWAP_THREADS / 32; ++w) {
+    const int c = wsum[w];
+    if (w < warp) before += c;
+    tot += c;
+  }
+  total = tot;
+  return before + inc - v;
+}
+__global__ void __launch_bounds__(WG_SWAP_THREADS) wg_pool_swap_kernel(const Dev d, const PoolDev p,
+                                                                       const uint8_t* __restrict__ truncated,
+                                                                       uint8_t* __restrict__ swapped) {
+  __shared__ int wsum[WG_SWAP_THREADS / 32];
   __shared__ int s_src[WG_POOL_MAX_SWAP], s_dst[WG_POOL_MAX_SWAP];
   const int tid = threadIdx.x;
-  // ordered compaction (block scan, not atomics): the k-th ready spare goes to the k-th finished env, run after run
   int nsrc = 0, ndst = 0, nneed = 0;
-  for (int base = p.n_active; base < p.B; base += 1024) {
-    const int b = base + tid;
-    int flag = 0, need = 0;
-    if (b < p.B) {
-      int st = p.status[b];
-      if (st == POOL_PENDING) { p.status[b] = POOL_NEED; st = POOL_NEED; }
-      flag = st == POOL_READY;
-      need = st == POOL_NEED;
+  // spares: 4 slots per thread and pass
+  for (int base = p.n_active; base < p.B; base += 4 * WG_SWAP_THREADS) {
+    int mine[4], cnt = 0, need = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int b = base + 4 * tid + k;
+      mine[k] = -1;
+      if (b < p.B) {
+        int st = p.status[b];
+        if (st == POOL_PENDING) { p.status[b] = POOL_NEED; st = POOL_NEED; }
+        if (st == POOL_READY) { mine[k] = b; ++cnt; }
+        need += st == POOL_NEED;
+      }
     }
-    scan[tid] = flag;
-    const int total = __syncthreads_count(flag);
-    nneed += __syncthreads_count(need);
-    plan_exclusive_scan(scan, wsum);
-    if (flag && nsrc + scan[tid] < WG_POOL_MAX_SWAP) s_src[nsrc + scan[tid]] = b;
+    int total, tneed;
+    int at = nsrc + swap_block_excl_scan(cnt, wsum, total);
+    swap_block_excl_scan(need, wsum, tneed);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (mine[k] >= 0) { if (at < WG_POOL_MAX_SWAP) s_src[at] = mine[k]; ++at; }
     nsrc += total;
-    __syncthreads();
+    nneed += tneed;
   }
-  for (int base = 0; base < p.n_active; base += 1024) {
-    const int b = base + tid;
-    int flag = 0;
-    if (b < p.n_active) { swapped[b] = 0; flag = truncated[b] != 0; }
-    scan[tid] = flag;
-    const int total = __syncthreads_count(flag);
-    plan_exclusive_scan(scan, wsum);
-    if (flag && ndst + scan[tid] < WG_POOL_MAX_SWAP) s_dst[ndst + scan[tid]] = b;
+  // finished episodes: 16 envs per thread and pass, flags read four at a time
+  const bool al4 = (((uintptr_t)truncated | (uintptr_t)swapped) & 3) == 0;
+  for (int base = 0; base < p.n_active; base += 16 * WG_SWAP_THREADS) {
+    const int b0 = base + 16 * tid;
+    unsigned bits = 0;  // bit k: env b0 + k finished
+    if (al4 && b0 + 16 <= p.n_active) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const unsigned w = reinterpret_cast<const unsigned*>(truncated + b0)[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits |= ((w >> (8 * k)) & 0xffu) ? 1u << (4 * q + k) : 0u;
+        reinterpret_cast<unsigned*>(swapped + b0)[q] = 0u;
+      }
+    } else {
+      for (int k = 0; k < 16; ++k)
+        if (b0 + k < p.n_active) { bits |= truncated[b0 + k] ? 1u << k : 0u; swapped[b0 + k] = 0; }
+    }
+    int total;
+    int at = ndst + swap_block_excl_scan(__popc(bits), wsum, total);
+    while (bits) {
+      const int k = __ffs(bits) - 1;
+      bits &= bits - 1;
+      if (at < WG_POOL_MAX_SWAP) s_dst[at] = b0 + k;
+      ++at;
+    }
     ndst += total;
-    __syncthreads();
   }
+  __syncthreads();
   const int n = min(min(nsrc, ndst), WG_POOL_MAX_SWAP);
   if (tid < n) {
     const int src = s_src[tid], dst = s_dst[tid];
@@ -734,18 +782,33 @@ __global__ void __launch_bounds__(1024) wg_pool_swap_kernel(const Dev d, const P
   }
 }
 
-// Copy the paired spares over the finished envs: grid (chunks, 8 pair lanes); no pairs: nothing to do.
-// The finished env's last observation is kept in final_obs (the "terminal observation" of the vector-env APIs), its
-// observation row then becomes the spare's reset observation.
+// Copy the paired spares over the finished envs: grid (chunks, state fields + 1, pair lanes) -- one CTA per (chunk of
+// a field, lane of pairs), so that the ~45 fields of an env move side by side (a CTA that walks the field list pays
+// a dependent global load per field: measured 40 us per step); no pairs: every CTA reads n and leaves.  Field index
+// n_fields is the observation row: the finished episode's last observation is kept in final_obs (the "terminal
+// observation" of the vector-env APIs), the row then becomes the spare's reset observation.
 __global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __restrict__ state, const CopyField* __restrict__ fields,
                                                            int n_fields, const PoolDev p, float* __restrict__ obs,
                                                            float* __restrict__ final_obs, int obs_floats) {
   const int n = p.swap[2 * WG_POOL_MAX_SWAP];
+  if (n == 0) return;
   const unsigned nchunk = gridDim.x, chunk = blockIdx.x;
-  for (int k = blockIdx.y; k < n; k += gridDim.y) {
-  const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
-  for (int fi = 0; fi < n_fields; ++fi) {
-    const CopyField f = fields[fi];
+  const int fi = blockIdx.y;
+  if (fi == n_fields) {
+    if (chunk) return;
+    for (int k = blockIdx.z; k < n; k += gridDim.z) {
+      const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
+      for (int i = threadIdx.x; i < obs_floats; i += blockDim.x) {
+        if (final_obs) final_obs[(size_t)dst * obs_floats + i] = obs[(size_t)dst * obs_floats + i];
+        obs[(size_t)dst * obs_floats + i] = obs[(size_t)src * obs_floats + i];
+      }
+    }
+    return;
+  }
+  const CopyField f = fields[fi];
+  if ((size_t)chunk * blockDim.x * 16 >= f.per_env && chunk) return;  // small field: chunk 0 does it all
+  for (int k = blockIdx.z; k < n; k += gridDim.z) {
+    const int src = p.swap[k], dst = p.swap[WG_POOL_MAX_SWAP + k];
     const size_t so = (size_t)src * f.per_env, dof = (size_t)dst * f.per_env;
     for (unsigned r = 0; r < f.n_rep; ++r) {
       unsigned char* base = state + f.offset + (size_t)r * f.rep_stride;
@@ -760,12 +823,6 @@ __global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __rest
       }
     }
   }
-  if (chunk == 0)
-    for (int i = threadIdx.x; i < obs_floats; i += blockDim.x) {
-      if (final_obs) final_obs[(size_t)dst * obs_floats + i] = obs[(size_t)dst * obs_floats + i];
-      obs[(size_t)dst * obs_floats + i] = obs[(size_t)src * obs_floats + i];
-    }
-  }
 }
 
 cudaError_t launch_pool_claim(const Dev& d, const PoolDev& p, const PoolDraw& w, int mask_row, cudaStream_t s) {
@@ -777,12 +834,12 @@ cudaError_t launch_pool_publish(const PoolDev& p, int mask_row, cudaStream_t s) 
   return cudaGetLastError();
 }
 cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* truncated, uint8_t* swapped, cudaStream_t s) {
-  wg_pool_swap_kernel<<<1, 1024, 0, s>>>(d, p, truncated, swapped);
+  wg_pool_swap_kernel<<<1, WG_SWAP_THREADS, 0, s>>>(d, p, truncated, swapped);
   return cudaGetLastError();
 }
 cudaError_t launch_pool_copy(unsigned char* state, const CopyField* fields, int n_fields, const PoolDev& p, float* obs,
                              float* final_obs, int obs_floats, cudaStream_t s) {
-  wg_pool_copy_kernel<<<dim3(32, 8), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
+  wg_pool_copy_kernel<<<dim3(16, n_fields + 1, 4), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
   return cudaGetLastError();
 }
 

@@ -233,7 +233,10 @@ class DevicePooledVecEnv:
         self.x_pos, self.y_pos = v.x_pos, v.y_pos
         self.lib = v.lib
         n_streams = min(max(1, int(n_streams)), 8)          # one refill mask row per stream (WG_POOL_MASKS)
-        self._bgs = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        # HIGH priority: a refill is a few dozen long-lived CTAs; behind a stepping grid that always has thousands of CTAs
+        # queued they would wait for slots and the spin-up latency (hence the number of spares in flight) would grow
+        # without bound -- with priority they take their slots at once and the stepping grid fills the rest
+        self._bgs = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(n_streams)]
         self._bg_events = [None] * n_streams
         self._n_refill = 0
         self._n_tried = 0
@@ -245,6 +248,9 @@ class DevicePooledVecEnv:
         self.swapped = torch.zeros(B + self.reserve, dtype=torch.uint8, device=self.device)
         self._final = torch.zeros_like(v.obs)
         self._ready = False
+        self._swap_ptrs = (v._step_ptrs[0], v._step_ptrs[3], v._step_ptrs[1], C.c_void_p(self.swapped.data_ptr()),
+                           C.c_void_p(self._final.data_ptr()))
+        self._views = (v.obs[:B], v.reward[:B], v.terminated[:B], self.swapped[:B])
 
     # ------------------------------------------------------------------------------------------ protocol
     @property
@@ -381,13 +387,14 @@ class DevicePooledVecEnv:
     def step(self, actions):
         if not self._ready:
             raise RuntimeError("reset() must be called before step()")
-        v, B = self.inner, self.n_envs
-        obs, rew, term, trunc, _ = v.step(actions)
-        rc = self.lib.wg_pool_swap(v._h, v._step_ptrs[0], v._step_ptrs[3], v._step_ptrs[1], self.swapped.data_ptr(),
-                                   self._final.data_ptr(), v._stream())
+        v = self.inner
+        v.step(actions, info=False)
+        sp = self._swap_ptrs
+        rc = self.lib.wg_pool_swap(v._h, sp[0], sp[1], sp[2], sp[3], sp[4], v._stream())
         if rc != 0:
             self._lib_mod.check(rc)
         self._steps += 1
         if self._steps % self.refill_every == 0:
             self._refill()
-        return obs[:B], rew[:B], term[:B], self.swapped[:B], self._info()
+        o = self._views          # fixed buffers: the sliced views are built once
+        return o[0], o[1], o[2], o[3], self._info()

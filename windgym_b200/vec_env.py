@@ -349,8 +349,9 @@ class VecWindFarmEnv:
         self.time_max = time_max
         return self.obs, self._info()
 
-    def step(self, actions):
-        """WindFarmEnv.step for every env: actions float32 [B,T] (device) -> obs, reward, terminated, truncated, info."""
+    def step(self, actions, info=True):
+        """WindFarmEnv.step for every env: actions float32 [B,T] (device) -> obs, reward, terminated, truncated, info
+        (``info=False``: None instead of the dict of live device views, for wrappers that build their own)."""
         if not torch.is_tensor(actions):
             actions = torch.as_tensor(np.asarray(actions, dtype=np.float32))
         if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
@@ -364,7 +365,7 @@ class VecWindFarmEnv:
         if rc != 0:
             _lib.check(rc)
         self._last_actions = actions   # keeps the tensor alive until the launch has consumed it
-        return self.obs, self.reward, self.terminated, self.truncated, self._info()
+        return self.obs, self.reward, self.terminated, self.truncated, (self._info() if info else None)
 
     def step_host(self, actions):
         """``step()`` for callers whose buffers live on the HOST (the reference's contract: numpy in, numpy out):

@@ -27,6 +27,36 @@ from .envs import Box
 from .vec_env import VecWindFarmEnv
 
 
+class _LazyInfos(dict):
+    """Info dict whose farm power sums are evaluated on first access (one torch reduction each)."""
+
+    _LAZY = {"Power agent": "Power pr turbine agent", "Power baseline": "Power pr turbine baseline"}
+
+    def __init__(self, raw, baseline):
+        super().__init__(raw)
+        self._pending = {"Power agent"} | ({"Power baseline"} if baseline else set())
+
+    def __missing__(self, key):
+        if key in self._pending:
+            self._pending.discard(key)
+            val = dict.__getitem__(self, self._LAZY[key]).sum(dim=1)
+            self[key] = val
+            return val
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._pending
+
+    def keys(self):
+        for k in list(self._pending):
+            self[k]
+        return dict.keys(self)
+
+    def items(self):
+        self.keys()
+        return dict.items(self)
+
+
 class _VectorBase:
     metadata = {"render_modes": [], "autoreset_mode": "same_step"}
     render_mode = None
@@ -64,9 +94,14 @@ class _VectorBase:
         return a.astype(dtype) if dtype is not None else a
 
     def _infos(self):
-        """Dict-of-arrays info with the reference's keys (Wind_Farm_Env.py:527-555), batched on axis 0."""
+        """Dict-of-arrays info with the reference's keys (Wind_Farm_Env.py:527-555), batched on axis 0.  With
+        ``as_torch`` the entries are the env's live device views and the farm power sums (``"Power agent"``, the array
+        ``RecordEpisodeVals`` reads, ``"Power baseline"``) are computed when first read: a rollout loop that does not
+        look at the infos launches no extra kernel per step."""
         v = self.venv
         raw = v._info()
+        if self.as_torch:
+            return _LazyInfos(raw, v.Baseline_comp)
         out = {}
         for k, val in raw.items():
             out[k] = self._out(val) if torch.is_tensor(val) else np.asarray(val)
@@ -119,10 +154,11 @@ class GymVectorEnv(_VectorBase):
         obs, rew, term, trunc, infos, final_obs, done = self._step_core(actions)
         if final_obs is not None:
             infos["final_observation"] = self._out(final_obs)
-            infos["_final_observation"] = (done.bool() if self.as_torch else done.cpu().numpy().astype(bool)) \
+            infos["_final_observation"] = ((done.view(torch.bool) if done.dtype == torch.uint8 else done.bool())
+                                           if self.as_torch else done.cpu().numpy().astype(bool)) \
                 if torch.is_tensor(done) else done
         if self.as_torch:
-            return obs, rew, term, trunc.bool(), infos
+            return obs, rew, term, (trunc.view(torch.bool) if trunc.dtype == torch.uint8 else trunc.bool()), infos
         return (obs.cpu().numpy(), rew.cpu().numpy().astype(np.float64), term.cpu().numpy(),
                 trunc.cpu().numpy().astype(bool), infos)
 
