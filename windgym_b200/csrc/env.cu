@@ -383,7 +383,9 @@ static cudaError_t launch_finish_as(const Dev& d, const FinishArgs& a, cudaStrea
 
 // envs of one wave of the two-warps-per-env variant (4 CTAs of 4 envs per SM on 148 SMs): below this the kernel is pure
 // latency and the variant pays; above it the one-warp variant keeps the whole batch in a single wave
+#ifndef WG_FIN_PAIR_MAX
 #define WG_FIN_PAIR_MAX 2048
+#endif
 
 cudaError_t launch_finish(const Dev& d, const FinishArgs& a, cudaStream_t s) {
   const size_t smem = sizeof(float) * WG_FIN_WARPS * (((size_t)d.ring_floats + 2 * (size_t)d.power_avg + 3) & ~(size_t)3);

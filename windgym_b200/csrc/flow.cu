@@ -554,7 +554,10 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #endif
 
 template <int TC, int TURB>
-__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? 5 : 6) : 4)
+#ifndef WG_TURB_CTAS
+#define WG_TURB_CTAS 5
+#endif
+__global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS : 6) : 4)
     wg_flow_kernel(const Dev d, const FlowArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // rows must be 256-byte aligned (XOR addressing)
   typedef FlowShared<TC, TURB> Shared;
