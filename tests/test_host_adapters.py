@@ -215,3 +215,25 @@ def test_shipped_ppo_zip_loads_with_from_zip():
             with zipfile.ZipFile(f.name, "w") as zz:
                 zz.writestr("data", "{}")
             SB3MlpPolicy.from_zip(f.name)
+
+
+def test_lazy_infos_compute_power_sums_on_first_read():
+    """as_torch adapters hand out the env's live info views; the farm power sums cost a reduction each and are only
+    evaluated when somebody reads them (RecordEpisodeVals does, a bare rollout loop does not)."""
+    from windgym_b200.vector import _LazyInfos
+    p = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    raw = {"Power pr turbine agent": p, "Power pr turbine baseline": 2 * p, "Wind speed Global": np.ones(3)}
+    inf = _LazyInfos(raw, baseline=True)
+    assert "Power agent" in inf and "Power baseline" in inf and "nope" not in inf
+    assert not dict.__contains__(inf, "Power agent")                   # not computed yet
+    assert torch.equal(inf["Power agent"], p.sum(dim=1)) and dict.__contains__(inf, "Power agent")
+    assert set(inf.keys()) == set(raw) | {"Power agent", "Power baseline"}
+    assert torch.equal(dict(inf.items())["Power baseline"], 2 * p.sum(dim=1))
+    with pytest.raises(KeyError):
+        inf["nope"]
+    assert "Power baseline" not in _LazyInfos(raw, baseline=False)
+    fake = FakeVecEnv(4, n_turb=3, horizon=50)
+    env = GymVectorEnv(venv=fake, as_torch=True)
+    env.reset()
+    _, _, _, trunc, infos = env.step(torch.zeros((4, 3)))
+    assert trunc.dtype == torch.bool and infos["Power agent"].shape == (4,)

@@ -851,13 +851,18 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
         }
         count_below2(sh.xs, xs_top, xn, xe, cn, ce);
       };
-      if (!TURB) move_and_search();
+#ifdef WG_EXP_TURB_EARLY
+      const bool early = !TURB || tile != tile0;   // bricks of later tiles were prefetched a round ahead: L2 hits
+#else
+      const bool early = !TURB;
+#endif
+      if (early) move_and_search();
       if (TURB && tile == tile0 && Lc.valid) prefetch_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo);  // later tiles: a round ahead
       WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches, moves, plane searches
       mbar_wait(bar, phase);
       phase ^= 1u;
       WG_PHASE(2)  // waiting for the tile
-      if (TURB) move_and_search();
+      if (!early) move_and_search();
       const float u0cg = pcc.x * pcc.z, u0sg = pcc.x * pcc.w;
       {  // warp-collective TMEM traffic: idle lanes march their (stale) row too
         const float xt_mid = (pmc.x + 0.5f * dx - sh.xr[Lc.chain]) * rR;
