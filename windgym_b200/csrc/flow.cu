@@ -851,11 +851,9 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
         }
         count_below2(sh.xs, xs_top, xn, xe, cn, ce);
       };
-#ifdef WG_EXP_TURB_EARLY
-      const bool early = !TURB || tile != tile0;   // bricks of later tiles were prefetched a round ahead: L2 hits
-#else
+      // (with a box, running the block before the wait -- the later tiles' bricks are L2 hits thanks to the round-ahead
+      // prefetch -- was measured again with the brick layout: 0.546 vs 0.538 ms, still slower)
       const bool early = !TURB;
-#endif
       if (early) move_and_search();
       if (TURB && tile == tile0 && Lc.valid) prefetch_lp(d, pmc.x, pmc.y, pmc.z, xs_t, tb_yo, tb_zo);  // later tiles: a round ahead
       WG_PHASE(1)  // tile set-up: segments, load issue, scalars, prefetches, moves, plane searches
