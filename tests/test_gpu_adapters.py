@@ -308,3 +308,44 @@ def test_two_gpus_driven_by_one_process(built_lib):
             env.close()
     assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
     assert np.isfinite(outs[0][0]).all() and outs[0][1].max() > 1e5
+
+
+def test_sb3_vec_env_and_ppo_rollout_on_the_device_pool(built_lib):
+    """The adapters as a training loop uses them, on the default device-side pool: SB3VecEnv (numpy out, list of info
+    dicts with terminal_observation / TimeLimit.truncated) and collect_rollout with per-agent observations (BASELINE.json
+    cfg 5's PPO-rollout shape) through real episode ends -- no masked reset, no stall."""
+    import torch
+    from windgym_b200 import DevicePooledVecEnv, SB3VecEnv, V80
+    from windgym_b200.vector import collect_rollout
+    cfg = small_config(2, 1, reward="Power_avg", action="yaw")
+    B, T = 5, 2
+    env = SB3VecEnv(V80(), B, config=cfg, n_passthrough=0.2, seed=2, device="cuda:0", reserve=8, refill_every=1)
+    assert isinstance(env.venv, DevicePooledVecEnv)
+    obs = env.reset()
+    assert obs.shape == (B, 4) and obs.dtype == np.float32
+    n_done, saw_terminal = 0, False
+    for k in range(40):
+        obs, rew, dones, infos = env.step(np.zeros((B, T), dtype=np.float32))
+        assert obs.shape == (B, 4) and rew.shape == (B,) and dones.dtype == bool and len(infos) == B
+        assert np.isfinite(obs).all() and np.isfinite(rew).all()
+        for i in range(B):
+            assert infos[i]["TimeLimit.truncated"] == bool(dones[i])
+            if dones[i]:
+                n_done += 1
+                saw_terminal = True
+                assert infos[i]["terminal_observation"].shape == (4,) and np.isfinite(infos[i]["terminal_observation"]).all()
+            assert infos[i]["Power agent"] > 0
+    assert n_done >= 5 and saw_terminal
+    env.close()
+    # multi-agent rollout buffers on the pool: obs [n, B, T, obs], one action per agent, dones where episodes ended
+    pool = DevicePooledVecEnv(V80(), 6, config=small_config(2, 2, reward="Power_avg", action="yaw"), multi_agent=True,
+                              n_passthrough=0.3, seed=4, device="cuda:0", reserve=12, refill_every=1)
+    pool.reset(seed=4)
+    ro = collect_rollout(pool, lambda o: torch.tanh(o.sum(dim=-1)), 48)
+    assert tuple(ro["obs"].shape) == (48, 6, 4, 2) and tuple(ro["actions"].shape) == (48, 6, 4)
+    assert bool(torch.isfinite(ro["obs"]).all()) and bool(torch.isfinite(ro["rewards"]).all())
+    assert int(ro["dones"].sum()) >= 6                      # every env finished at least about once
+    st = pool.stats
+    assert st["swapped"] == int(ro["dones"].sum()) and st["refilled"] >= st["swapped"]
+    pool.check_flags()
+    pool.close()
