@@ -317,3 +317,40 @@ def test_measurement_noise_normal_distribution_and_seeding(built_lib):
     # identical envs draw independent noise: across-env correlation of the noise ~ 0, and no two envs share a sample
     a, b = noise_deg[:, 0].ravel(), noise_deg[:, 1].ravel()
     assert abs(np.corrcoef(a, b)[0, 1]) < 0.25 and len(np.unique(np.round(noise_deg[0], 6))) > 0.98 * B * T
+
+
+@pytest.mark.parametrize("B,reward", [(200, "Baseline"), (1100, "Power_avg")])
+def test_free_running_steps_overlap_the_previous_finish_kernel(built_lib, monkeypatch, B, reward):
+    """Steps issued back to back without a host synchronisation: the flow kernel of step k+1 is launched as
+    programmatic dependent of step k's finish kernel (its prologue and tile loop overlap it, griddepcontrol.wait in
+    front of the turbine epilogue).  Results -- every observation / reward of the rollout, the wake state at the end --
+    must be bit-identical to plain stream order (WG_NO_PDL_NEXT=1), for a batch below one wave of CTAs (work table,
+    both PDL edges) and above it, with one and two farms per env."""
+    import torch
+    from windgym_b200 import V80, VecWindFarmEnv
+    cfg = small_config(3, 2, reward=reward, action="yaw")
+    T, steps = 6, 150
+    ws, ti, wd, yaw0 = _conditions(B, T, seed=23)
+    acts = torch.as_tensor(np.random.default_rng(8).uniform(-1, 1, (steps, B, T)).astype(np.float32)).cuda()
+
+    def rollout():
+        env = VecWindFarmEnv(V80(), B, config=cfg, device="cuda:0", n_passthrough=50)
+        env.reset(wind=(ws, ti, wd), yaw0=yaw0)
+        obs = torch.empty((steps, B, env.obs_var), device="cuda:0")
+        rew = torch.empty((steps, B), device="cuda:0")
+        for k in range(steps):                      # no read-back inside the loop: the launches run ahead of the device
+            o, r, _, _, _ = env.step(acts[k], info=False)
+            obs[k].copy_(o); rew[k].copy_(r)
+        torch.cuda.synchronize()
+        env.check_flags()
+        st = {k: env.state[k].clone() for k in ("prof", "pmut", "pcon", "yaw", "power", "count", "head", "rings")}
+        env.close()
+        return obs.cpu().numpy(), rew.cpu().numpy(), st
+
+    obs_a, rew_a, st_a = rollout()
+    monkeypatch.setenv("WG_NO_PDL_NEXT", "1")       # read at wg_create
+    obs_b, rew_b, st_b = rollout()
+    assert np.isfinite(obs_a).all() and np.abs(obs_a).max() > 0
+    assert np.array_equal(obs_a, obs_b) and np.array_equal(rew_a, rew_b)
+    for k in st_a:
+        assert torch.equal(st_a[k], st_b[k]), f"state field {k} differs"

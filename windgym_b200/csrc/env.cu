@@ -146,6 +146,10 @@ __global__ void __launch_bounds__(WG_FIN_WARPS * 32 * (PAIR ? 2 : 1), PAIR ? 4 :
   // of it written by the flow kernel) ran while the flow grid was still draining; its results (substep means, baseline
   // power, yaws) are read from here on.  Without the launch attribute the wait returns at once.
   if (a.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+  // The next step's flow kernel may start now (FlowArgs::pdl_wait): the flow grid of THIS step is complete (waited for
+  // above, or ordinary stream order), and the next one touches nothing this kernel reads or writes before its own
+  // griddepcontrol.wait.
+  if (a.trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float g_base_pow = d.base_pow_mean[b];
   if (a.flags & (FIN_PUSH_MES | FIN_PUSH_FP))
     for (int t = lane_e; t < T; t += n_e) {

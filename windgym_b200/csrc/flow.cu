@@ -981,6 +981,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
       WG_PHASE(5)  // waiting for the store to release the buffer
     }
     WG_STAMP(t_p3);
+    // Programmatic dependent of the previous step's finish kernel: from here on the CTA writes what that kernel reads
+    // (substep means, yaws, powers, baseline power) -- wait for it to be complete.  Everything above touched the wake
+    // state only.  (Without the launch attribute, or behind a kernel that never triggers, the wait returns at once.)
+    if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (nparts > 1) {
       // Split farm: add this CTA's sums to the farm's global ones and take an arrival ticket.  Every part but the last
       // to arrive is done (its rows and station scalars are on their way to HBM); the last one collects the sums --
@@ -1214,6 +1218,15 @@ static cudaError_t launch_as(const Dev& d, const FlowArgs& a, cudaStream_t s) {
     if (dev >= 0 && dev < WG_MAX_DEVICES) configured[dev] = true;
   }
   const int grid = a.work ? a.n_work : d.Bg * d.F;
+  if (a.pdl_wait) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(WG_NWARP * 32); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, wg_flow_kernel<TC, TURB>, d, a);
+  }
   wg_flow_kernel<TC, TURB><<<grid, WG_NWARP * 32, smem, s>>>(d, a);
   return cudaGetLastError();
 }

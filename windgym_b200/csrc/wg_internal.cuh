@@ -134,6 +134,9 @@ struct FlowArgs {
   int n_work;           // entries of the table = CTAs of the launch
   int pdl_trigger;      // every CTA releases the dependent launch (the step's finish kernel) at its start: the batch
                         // leaves CTA slots free, so the finish grid's launch and staging overlap the flow grid's tail
+  int pdl_wait;         // launched as programmatic dependent of the PREVIOUS step's finish kernel: prologue and tile
+                        // loop (wake state only: nothing the finish kernel touches) overlap it; griddepcontrol.wait
+                        // in front of the turbine epilogue (substep means, yaws, powers: what the finish kernel reads)
 };
 
 // how wg_plan_kernel cuts the farms of a step into CTAs
@@ -158,6 +161,7 @@ struct FinishArgs {
   volatile unsigned* done_flag;  // mapped host word
   unsigned seq;
   int pdl;                       // launched as programmatic dependent of the flow kernel (griddepcontrol.wait inside)
+  int trigger;                   // releases the NEXT step's flow kernel (FlowArgs::pdl_wait) once the flow results are in
 };
 
 // Device-side spare pool (wg_pool_*): status of every env slot
