@@ -208,7 +208,10 @@ def bench_config(a, envs_per_rank, where, world=1):
             "farms_per_env": 2 if a.reward == "Baseline" else 1, "power_reward": a.reward,
             "dt_env": 1, "dt_sim": 1, "obs_dim": 2 * a.nx * a.ny, "parallelism": f"env-sharded x{a.gpus}",
             "turbtype": getattr(a, "turbtype", "None"),
-            "l2_policy": "working set (wake state, >= 200 MB per step and GPU) exceeds the 126 MB L2; no explicit flush"}
+            "l2_policy": "working set (wake state, >= 200 MB per step and GPU) exceeds the 126 MB L2; no explicit flush",
+            "step_overlap": "free-running timed loop: each step's flow kernel is a programmatic dependent launch of the "
+                            "previous step's finish kernel (its wake-advection part overlaps it; bit-identical results); "
+                            "e2e waits for every step's results on the host, no overlap there"}
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
