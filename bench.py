@@ -306,6 +306,9 @@ def measure(torch, dist, env, acts_host, K, W, K_e2e, K_prof, world, extra_bytes
                      "finish_kernel_ms": t_fin_ms, "live_stations_per_env_farm": live_all / (B_all * F),
                      "bytes_per_station": STATION_BYTES + extra_bytes_per_station,
                      "algorithmic_bytes_per_launch_per_gpu": bytes_flow / world, "launches_timed": int(n_prof),
+                     # SURVEY 8(d) "for the fused step": the same bytes over the whole device step of the timed loop
+                     "step_achieved": bytes_flow / world / (t_ms / K * 1e-3) / 1e9,
+                     "step_frac": bytes_flow / world / (t_ms / K * 1e-3) / 1e9 / peak,
                      "per": "GPU (bytes of all ranks / n_gpus / max-over-ranks launch time)"},
     }
 
