@@ -126,7 +126,10 @@ const char* wg_state_field_name(const wg_handle* h, int32_t index);
 int wg_reset(wg_handle* h, void* state, const wg_reset_args* args, float* obs, void* cuda_stream);
 
 /* WindFarmEnv.step (Wind_Farm_Env.py:920-1034) for all envs.  actions: device [B,T] in [-1,1].
- * reward: device [B]; truncated: device [B] (terminated is always False in the reference, :1029). */
+ * reward: device [B]; truncated: device [B] (terminated is always False in the reference, :1029).
+ * Asynchronous: the kernels are enqueued on cuda_stream and the results are complete, in stream order, when the
+ * step's last kernel is.  Consecutive steps on one stream overlap where their data allow (programmatic dependent
+ * launch: the next step's wake advection runs beside this step's observation kernel); results do not depend on it. */
 int wg_step(wg_handle* h, void* state, const float* actions, float* obs, float* reward, uint8_t* truncated,
             void* cuda_stream);
 

@@ -17,7 +17,11 @@
 //     cp.async.bulk shared -> HBM
 // then the per-turbine epilogue (P/CT tables, particle release) runs in the same CTA, and the substep loop
 // (dt_env/dt_sim, or a whole spin-up) repeats without leaving the kernel.  wg_step launches the envs longest first
-// (FlowArgs::order); the stations a step retires were found by the lanes that marched them in the previous one.
+// (FlowArgs::order) or, for single-substep steps, through a work table that cuts farms into parts when the batch
+// leaves CTA slots free (FlowArgs::work); the stations a step retires were found by the lanes that marched them in
+// the previous one.  Launch edges: the step's finish kernel is a programmatic dependent of this kernel below one
+// wave of CTAs (pdl_trigger), and this kernel is a programmatic dependent of the PREVIOUS step's finish kernel
+// (pdl_wait: everything up to the turbine epilogue touches the wake state only and overlaps it).
 // Algorithmic traffic per station and step: 256 B profile + 16 B mutable + 16 B emission scalars read,
 // 256 B + 16 B written = 560 B.  HBM/issue bound; no tensor cores (stencil + gather).
 //
