@@ -323,9 +323,10 @@ def test_measurement_noise_normal_distribution_and_seeding(built_lib):
 def test_free_running_steps_overlap_the_previous_finish_kernel(built_lib, monkeypatch, B, reward):
     """Steps issued back to back without a host synchronisation: the flow kernel of step k+1 is launched as
     programmatic dependent of step k's finish kernel (its prologue and tile loop overlap it, griddepcontrol.wait in
-    front of the turbine epilogue).  Results -- every observation / reward of the rollout, the wake state at the end --
-    must be bit-identical to plain stream order (WG_NO_PDL_NEXT=1), for a batch below one wave of CTAs (work table,
-    both PDL edges) and above it, with one and two farms per env."""
+    front of the turbine epilogue); the finish kernel in turn is a programmatic dependent of the step's flow kernel
+    (released at CTA start below one wave of CTAs, behind the tile loops above).  Results -- every observation / reward
+    of the rollout, the wake state at the end -- must be bit-identical to plain stream order (WG_NO_PDL=1), for a batch
+    below one wave of CTAs and above it, with one and two farms per env."""
     import torch
     from windgym_b200 import V80, VecWindFarmEnv
     cfg = small_config(3, 2, reward=reward, action="yaw")
@@ -348,9 +349,12 @@ def test_free_running_steps_overlap_the_previous_finish_kernel(built_lib, monkey
         return obs.cpu().numpy(), rew.cpu().numpy(), st
 
     obs_a, rew_a, st_a = rollout()
-    monkeypatch.setenv("WG_NO_PDL_NEXT", "1")       # read at wg_create
+    monkeypatch.setenv("WG_NO_PDL_NEXT", "1")       # read at wg_create: no edge across steps
+    obs_c, rew_c, st_c = rollout()
+    monkeypatch.setenv("WG_NO_PDL", "1")            # no programmatic launch at all: plain stream order
     obs_b, rew_b, st_b = rollout()
     assert np.isfinite(obs_a).all() and np.abs(obs_a).max() > 0
-    assert np.array_equal(obs_a, obs_b) and np.array_equal(rew_a, rew_b)
-    for k in st_a:
-        assert torch.equal(st_a[k], st_b[k]), f"state field {k} differs"
+    for o, r, st, what in ((obs_a, rew_a, st_a, "all edges"), (obs_c, rew_c, st_c, "flow -> finish edge only")):
+        assert np.array_equal(o, obs_b) and np.array_equal(r, rew_b), what
+        for k in st:
+            assert torch.equal(st[k], st_b[k]), f"{what}: state field {k} differs"

@@ -76,6 +76,7 @@ struct wg_handle {
   int fill_waves = 0;                 // WG_FILL_WAVES=k: below k waves of farms, equalised parts that fill the last wave
   bool two_wave = true;               // WG_NO_TWOWAVE=1: between 1 and 2 waves of farms, keep one CTA per farm
   bool pdl_next = true;               // WG_NO_PDL_NEXT=1: the next step's flow kernel waits for the whole finish kernel
+  bool pdl_late = true;               // WG_NO_PDL_LATE=1: multi-wave grids launch the finish kernel in plain stream order
   bool use_pdl = true;                // WG_NO_PDL=1: plain stream order between the flow and the finish kernel
   // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
   // number, and the pinned host ranges already identified (host base, device alias, bytes)
@@ -437,6 +438,8 @@ int wg_create(const wg_config* cfg, wg_handle** out) {
   if (const char* ss = getenv("WG_SLOT_SHARE")) h->slot_share = (float)atof(ss);
   const char* no_tw = getenv("WG_NO_TWOWAVE");
   h->two_wave = !(no_tw && no_tw[0] == '1');
+  const char* no_pl = std::getenv("WG_NO_PDL_LATE");
+  h->pdl_late = !(no_pl && no_pl[0] == '1');
   const char* no_pn = std::getenv("WG_NO_PDL_NEXT");
   h->pdl_next = !(no_pn && no_pn[0] == '1');
   const char* no_pdl = getenv("WG_NO_PDL");
@@ -633,6 +636,9 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   const bool pdl = by_table && h->use_pdl && d.Bg * d.F < h->slots && !h->profiling;
   if (by_table) { fa.work = d.work; fa.n_work = h->n_work; fa.pdl_trigger = pdl ? 1 : 0; }
   else fa.order = h->use_order ? d.order : nullptr;
+  // more farms than slots: the finish kernel is released behind the CTAs' tile loops
+  const bool pdl_late = !pdl && h->use_pdl && h->pdl_late && !h->profiling;
+  if (pdl_late) fa.pdl_trigger = 2;
   // the flow kernel of this step as programmatic dependent of the previous step's finish kernel (which triggers once
   // it holds the flow results): prologue + tile loop overlap it.  Behind any other kernel it is an ordinary launch.
   const bool pdl_chain = h->use_pdl && h->pdl_next && !h->profiling;
@@ -642,7 +648,7 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   wg::FinishArgs fin{};
   fin.flags = wg::FIN_PUSH_MES | wg::FIN_PUSH_FP | (d.F > 1 ? wg::FIN_PUSH_BP : 0) | wg::FIN_OBS | wg::FIN_REWARD;
   fin.obs = obs; fin.reward = reward; fin.truncated = truncated;
-  fin.pdl = pdl ? 1 : 0;
+  fin.pdl = (pdl || pdl_late) ? 1 : 0;
   fin.trigger = pdl_chain ? 1 : 0;
   if (host_out) {
     fin.obs_h = host_out->obs_h; fin.reward_h = host_out->reward_h; fin.truncated_h = host_out->truncated_h;

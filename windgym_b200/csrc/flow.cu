@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
   // relinquish -- 0.5 us when it is the first instruction, 2.9 us behind the prologue's loads).  Nothing loaded from
   // memory may be needed before this point (the work-table entry is first used below).
   if (warp == 0) tmem_alloc(&sh.tmem_base);
-  if (a.pdl_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (a.pdl_trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (bf < 0) {  // unused entry of the work table (CTA-uniform): give the columns back
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -985,6 +985,10 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
       WG_PHASE(5)  // waiting for the store to release the buffer
     }
     WG_STAMP(t_p3);
+    // multi-wave grids release the finish kernel here, behind the tile loop: it is launched while the last CTAs run
+    // their epilogues (its launch latency and ring staging are off the step's critical path) without taking CTA
+    // slots from the waves that still have to start (a trigger at CTA start does: measured slower)
+    if (a.pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     // Programmatic dependent of the previous step's finish kernel: from here on the CTA writes what that kernel reads
     // (substep means, yaws, powers, baseline power) -- wait for it to be complete.  Everything above touched the wake
     // state only.  (Without the launch attribute, or behind a kernel that never triggers, the wait returns at once.)

@@ -132,8 +132,9 @@ struct FlowArgs {
   const int* order;     // optional permutation of [0, Bg): CTA group i works on env order[i] (longest first)
   const int2* work;     // optional work table (single-step launches only): CTA i works on part work[i]; replaces order
   int n_work;           // entries of the table = CTAs of the launch
-  int pdl_trigger;      // every CTA releases the dependent launch (the step's finish kernel) at its start: the batch
-                        // leaves CTA slots free, so the finish grid's launch and staging overlap the flow grid's tail
+  int pdl_trigger;      // 1: every CTA releases the dependent launch (the step's finish kernel) at its start: the batch
+                        // leaves CTA slots free, so the finish grid's launch and staging overlap the flow grid's tail;
+                        // 2: ... behind its tile loop (multi-wave grids)
   int pdl_wait;         // launched as programmatic dependent of the PREVIOUS step's finish kernel: prologue and tile
                         // loop (wake state only: nothing the finish kernel touches) overlap it; griddepcontrol.wait
                         // in front of the turbine epilogue (substep means, yaws, powers: what the finish kernel reads)
