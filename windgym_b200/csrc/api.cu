@@ -77,6 +77,8 @@ struct wg_handle {
   bool two_wave = true;               // WG_NO_TWOWAVE=1: between 1 and 2 waves of farms, keep one CTA per farm
   bool pdl_next = true;               // WG_NO_PDL_NEXT=1: the next step's flow kernel waits for the whole finish kernel
   bool pdl_late = true;               // WG_NO_PDL_LATE=1: multi-wave grids launch the finish kernel in plain stream order
+  bool after_swap = false;            // wg_pool_swap came last: its copy kernel releases its dependents at its start, so
+                                      // the next flow launch waits at its top (FlowArgs::pdl_wait = 3) or is an ordinary one
   bool use_pdl = true;                // WG_NO_PDL=1: plain stream order between the flow and the finish kernel
   // wg_step_host, zero-copy path: completion word in mapped host memory + device arrival counter, step sequence
   // number, and the pinned host ranges already identified (host base, device alias, bytes)
@@ -642,7 +644,8 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   // the flow kernel of this step as programmatic dependent of the previous step's finish kernel (which triggers once
   // it holds the flow results): prologue + tile loop overlap it.  Behind any other kernel it is an ordinary launch.
   const bool pdl_chain = h->use_pdl && h->pdl_next && !h->profiling;
-  fa.pdl_wait = pdl_chain ? 1 : 0;
+  fa.pdl_wait = pdl_chain ? (h->after_swap ? 3 : 1) : 0;
+  h->after_swap = false;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
   if (ev) cudaEventRecord(ev[1], s);
   wg::FinishArgs fin{};
@@ -970,6 +973,7 @@ int wg_pool_swap(wg_handle* h, void* state, const uint8_t* truncated, float* obs
   cudaStream_t s = (cudaStream_t)cuda_stream;
   wg::Dev d = bind(h, state);
   wg::PoolDev p = bind_pool(h, state);
+  h->after_swap = true;
   WG_LAUNCH(wg::launch_pool_swap(d, p, truncated, swapped, s), "wg_pool_swap_kernel");
   WG_LAUNCH(wg::launch_pool_copy(reinterpret_cast<unsigned char*>(state), h->d_copy, h->n_copy, p, obs, final_obs,
                                  h->dev.obs_rows * h->dev.obs_dim, s),

@@ -718,6 +718,11 @@ __global__ void __launch_bounds__(WG_SWAP_THREADS) wg_pool_swap_kernel(const Dev
                                                                        uint8_t* __restrict__ swapped) {
   __shared__ int wsum[WG_SWAP_THREADS / 32];
   __shared__ int s_src[WG_POOL_MAX_SWAP], s_dst[WG_POOL_MAX_SWAP];
+  // Launched as programmatic dependent of the step's finish kernel (launch_pool_swap): only the launch latency
+  // overlaps -- the kernel waits for the finish grid to be complete before its first read, and releases the copy
+  // kernel's launch at once (that one waits for this grid in the same way).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int tid = threadIdx.x;
   int nsrc = 0, ndst = 0, nneed = 0;
   // spares: 4 slots per thread and pass
@@ -796,6 +801,8 @@ __global__ void __launch_bounds__(WG_SWAP_THREADS) wg_pool_swap_kernel(const Dev
 __global__ void __launch_bounds__(256) wg_pool_copy_kernel(unsigned char* __restrict__ state, const CopyField* __restrict__ fields,
                                                            int n_fields, const PoolDev p, float* __restrict__ obs,
                                                            float* __restrict__ final_obs, int obs_floats) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");               // the swap kernel's list (see there)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // next: the flow kernel, waiting at its top
   const int n = p.swap[2 * WG_POOL_MAX_SWAP];
   if (n == 0) return;
   const unsigned nchunk = gridDim.x, chunk = blockIdx.x;
@@ -839,14 +846,25 @@ cudaError_t launch_pool_publish(const PoolDev& p, int mask_row, cudaStream_t s) 
   wg_pool_publish_kernel<<<(p.B - p.n_active + 255) / 256, 256, 0, s>>>(p, mask_row);
   return cudaGetLastError();
 }
+// launch with programmatic stream serialization: the grid may be scheduled while its predecessor in the stream is
+// still running; the kernels wait (griddepcontrol.wait) before they touch memory
+template <class... KArgs, class... Args>
+static cudaError_t launch_programmatic(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 cudaError_t launch_pool_swap(const Dev& d, const PoolDev& p, const uint8_t* truncated, uint8_t* swapped, cudaStream_t s) {
-  wg_pool_swap_kernel<<<1, WG_SWAP_THREADS, 0, s>>>(d, p, truncated, swapped);
-  return cudaGetLastError();
+  return launch_programmatic(wg_pool_swap_kernel, dim3(1), dim3(WG_SWAP_THREADS), s, d, p, truncated, swapped);
 }
 cudaError_t launch_pool_copy(unsigned char* state, const CopyField* fields, int n_fields, const PoolDev& p, float* obs,
                              float* final_obs, int obs_floats, cudaStream_t s) {
-  wg_pool_copy_kernel<<<dim3(16, n_fields + 1, 4), 256, 0, s>>>(state, fields, n_fields, p, obs, final_obs, obs_floats);
-  return cudaGetLastError();
+  return launch_programmatic(wg_pool_copy_kernel, dim3(16, n_fields + 1, 4), dim3(256), s, state, fields, n_fields, p, obs,
+                             final_obs, obs_floats);
 }
 
 cudaError_t launch_copy_envs(unsigned char* state, const CopyField* fields, int n_fields, const int* src, const int* dst,

@@ -615,6 +615,8 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
   // memory may be needed before this point (the work-table entry is first used below).
   if (warp == 0) tmem_alloc(&sh.tmem_base);
   if (a.pdl_trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // behind the device pool's copy kernel (which rewrites whole envs): only the launch overlaps, wait before any load
+  if (a.pdl_wait == 3) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (bf < 0) {  // unused entry of the work table (CTA-uniform): give the columns back
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -992,7 +994,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
     // Programmatic dependent of the previous step's finish kernel: from here on the CTA writes what that kernel reads
     // (substep means, yaws, powers, baseline power) -- wait for it to be complete.  Everything above touched the wake
     // state only.  (Without the launch attribute, or behind a kernel that never triggers, the wait returns at once.)
-    if (a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (a.pdl_wait == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (nparts > 1) {
       // Split farm: add this CTA's sums to the farm's global ones and take an arrival ticket.  Every part but the last
       // to arrive is done (its rows and station scalars are on their way to HBM); the last one collects the sums --

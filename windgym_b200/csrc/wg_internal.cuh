@@ -135,9 +135,10 @@ struct FlowArgs {
   int pdl_trigger;      // 1: every CTA releases the dependent launch (the step's finish kernel) at its start: the batch
                         // leaves CTA slots free, so the finish grid's launch and staging overlap the flow grid's tail;
                         // 2: ... behind its tile loop (multi-wave grids)
-  int pdl_wait;         // launched as programmatic dependent of the PREVIOUS step's finish kernel: prologue and tile
+  int pdl_wait;         // 1: launched as programmatic dependent of the PREVIOUS step's finish kernel: prologue and tile
                         // loop (wake state only: nothing the finish kernel touches) overlap it; griddepcontrol.wait
-                        // in front of the turbine epilogue (substep means, yaws, powers: what the finish kernel reads)
+                        // in front of the turbine epilogue (substep means, yaws, powers: what the finish kernel reads);
+                        // 3: ... of the device pool's copy kernel: griddepcontrol.wait before the first load
 };
 
 // how wg_plan_kernel cuts the farms of a step into CTAs
