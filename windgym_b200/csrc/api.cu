@@ -644,7 +644,8 @@ static int step_impl(wg_handle* h, void* state, const float* actions, float* obs
   // the flow kernel of this step as programmatic dependent of the previous step's finish kernel (which triggers once
   // it holds the flow results): prologue + tile loop overlap it.  Behind any other kernel it is an ordinary launch.
   const bool pdl_chain = h->use_pdl && h->pdl_next && !h->profiling;
-  fa.pdl_wait = pdl_chain ? (h->after_swap ? 3 : 1) : 0;
+  // (a caller that waits for every step's results on the host -- wg_step_host -- has nothing to overlap: plain launch)
+  fa.pdl_wait = (pdl_chain && !host_out) ? (h->after_swap ? 3 : 1) : 0;
   h->after_swap = false;
   WG_LAUNCH(wg::launch_flow(d, fa, s), "wg_flow_kernel(step)");
   if (ev) cudaEventRecord(ev[1], s);
