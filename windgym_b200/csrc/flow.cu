@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(WG_NWARP * 32, TC <= 16 ? (TURB ? WG_TURB_CTAS
     // multi-wave grids release the finish kernel here, behind the tile loop: it is launched while the last CTAs run
     // their epilogues (its launch latency and ring staging are off the step's critical path) without taking CTA
     // slots from the waves that still have to start (a trigger at CTA start does: measured slower)
-    if (a.pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (a.pdl_trigger == 2 && sub + 1 == nsteps) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // last substep
     // Programmatic dependent of the previous step's finish kernel: from here on the CTA writes what that kernel reads
     // (substep means, yaws, powers, baseline power) -- wait for it to be complete.  Everything above touched the wake
     // state only.  (Without the launch attribute, or behind a kernel that never triggers, the wait returns at once.)
