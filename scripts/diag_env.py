@@ -7,7 +7,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from tests.helpers import oracle_rollout, small_config  # noqa: E402
+from tests.helpers import small_config  # noqa: E402
 from windgym_b200 import V80, VecWindFarmEnv  # noqa: E402
 
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 1561

@@ -16,7 +16,6 @@ Anything else (variable-length strings, compound types, virtual datasets, other 
 ``NotImplementedError`` naming ``scripts/convert_mann_netcdf.py`` as the way out.  Validated against the reference's own
 NetCDF-4 file ``examples/PPO_eval.nc`` (tests/test_host_logic.py, build container only) and a synthetic writer.
 """
-import struct
 import zlib
 
 import numpy as np
